@@ -1,0 +1,11 @@
+"""sid_lsg_b200: the SiD-LSG distillation step (SD UNet forwards/backwards, DDPM algebra, LSG losses, fused
+optimiser) on hand-written sm_100a CUDA behind a C ABI (include/sidlsg.h).  No CPU or PyTorch fallback:
+importing the ops without the built library raises."""
+from ._lib import lib, LIB_PATH  # noqa: F401
+from .unet import UNet2DConditionModel, UNetConfig, SD15, SD21_BASE, TINY, TINY_LINEAR  # noqa: F401
+from .scheduler import DDPMScheduler  # noqa: F401
+from .params import FlatParams  # noqa: F401
+from .training.sid_sd_util import sid_sd_sampler, sid_sd_denoise, PromptBatch  # noqa: F401
+from .training.step import SiDLSGStep, synth_microbatch, ema_beta  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,70 @@
+"""DDPMScheduler protocol on the sm_100a scheduler kernels.
+
+Replaces the diffusers DDPMScheduler object the reference drives at
+/root/reference/training/sid_sd_util.py:182-185 (add_noise, scale_model_input, step().pred_original_sample),
+:242-244, :262, :268-272 and /root/reference/training/sid_training_loop.py:425 (get_velocity).
+`scaled_linear` betas in [0.00085, 0.012], 1000 steps, epsilon prediction, clip_sample=False.
+The eps -> x0 conversion is batched over per-sample timesteps (the reference loops over samples in Python).
+"""
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+
+
+class _StepOutput:
+    def __init__(self, pred_original_sample):
+        self.pred_original_sample = pred_original_sample
+        self.prev_sample = None  # the reference discards prev_sample; it is never computed here
+
+
+class DDPMScheduler:
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, prediction_type="epsilon",
+                 device=None):
+        if prediction_type != "epsilon":
+            # v-prediction is dead code in the reference
+            raise NotImplementedError("only epsilon prediction (SD1.5, SD2.1-base) is on the SiD-LSG path")
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.config = SimpleNamespace(prediction_type=prediction_type, num_train_timesteps=num_train_timesteps,
+                                      clip_sample=False, variance_type="fixed_small")
+        self._acp_dev = {}
+        if device is not None:
+            self.acp(torch.device(device))
+
+    def acp(self, device):
+        key = str(device)
+        if key not in self._acp_dev:
+            self._acp_dev[key] = self.alphas_cumprod.to(device).contiguous()
+        return self._acp_dev[key]
+
+    @staticmethod
+    def _t(timesteps, like):
+        t = timesteps if torch.is_tensor(timesteps) else torch.tensor(timesteps)
+        t = t.to(device=like.device, dtype=torch.long).reshape(-1)
+        if t.numel() == 1 and like.shape[0] != 1:
+            t = t.expand(like.shape[0])
+        return t.contiguous()
+
+    def add_noise(self, original_samples, noise, timesteps):
+        return ops.add_noise(original_samples, noise.float(), self._t(timesteps, noise), self.acp(noise.device))
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=True):
+        """pred_original_sample = (x_t - sqrt(1-acp_t) eps) / sqrt(acp_t); `timestep` scalar or per-sample [B]."""
+        batched = model_output.dim() == 4
+        mo = model_output if batched else model_output[None]
+        sa = sample if batched else sample[None]
+        t = self._t(timestep, mo)
+        x0 = ops.cfg_x0(mo.float(), None, sa.float(), t, self.acp(mo.device), 1.0, True)
+        return _StepOutput(x0 if batched else x0[0])
+
+    def pred_x0(self, eps_uncond, eps_cond, x_t, timesteps, guidance_scale, predict_x0=True):
+        """fused CFG combine (+ eps -> x0) for a whole batch in one launch."""
+        t = self._t(timesteps, eps_uncond)
+        return ops.cfg_x0(eps_uncond, eps_cond, x_t, t, self.acp(eps_uncond.device), guidance_scale, predict_x0)

@@ -1,0 +1,145 @@
+"""One SiD-LSG iteration on the B200 kernels: fake-score update, generator update, EMA.
+
+Host orchestration of /root/reference/training/sid_training_loop.py:383-567; every arithmetic step is a kernel
+of libsidlsg.so.  Differences from the reference that do not change results:
+  * NaN rows are zero-weighted inside the fused loss kernels instead of being filtered by shape (App. B-6);
+  * nan_to_num + clip + Adam + EMA (+ bf16 shadow refresh) are ONE pass over the flat buckets;
+  * the data-parallel gradient mean is ONE NCCL allreduce per network per iteration on the flat gradient bucket
+    (the reference's DDP does the same reduction in 25 MiB buckets, :316-323), issued after the last
+    accumulation round (`ddp_sync` semantics, torch_utils/misc.py:168-175).
+"""
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from .sid_sd_util import PromptBatch, sid_sd_sampler, sid_sd_denoise
+
+
+def ema_beta(batch_size, cur_nimg, ema_halflife_kimg, ema_rampup_ratio=0.05):
+    """sid_training_loop.py:553-558."""
+    ema_halflife_nimg = ema_halflife_kimg * 1000
+    if ema_rampup_ratio is not None:
+        ema_halflife_nimg = min(ema_halflife_nimg, cur_nimg * ema_rampup_ratio)
+    return 0.5 ** (batch_size / max(ema_halflife_nimg, 1e-8))
+
+
+def _world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class SiDLSGStep:
+    """State + the two update phases.  `true_score`, `fake_score`, `G`, `G_ema` are UNet2DConditionModel
+    instances with flat buckets (the reference builds them with deepcopy, :284-287, 327)."""
+
+    def __init__(self, true_score, fake_score, G, G_ema, scheduler, *, lr=1e-6, glr=1e-6, betas=(0.0, 0.999),
+                 eps=1e-8, fp16=False, alpha=1.0, init_timestep=625, tmin=20, tmax=980, num_steps=1,
+                 cfg_train_fake=1.0, cfg_eval_fake=1.0, cfg_eval_real=1.0, loss_scaling=1.0, loss_scaling_G=1.0,
+                 ema_halflife_kimg=50, ema_rampup_ratio=0.05):
+        self.true_score, self.fake_score, self.G, self.G_ema = true_score, fake_score, G, G_ema
+        self.sched = scheduler
+        self.lr, self.glr, self.betas, self.eps, self.fp16 = lr, glr, betas, eps, fp16
+        self.alpha, self.init_timestep, self.tmin, self.tmax, self.num_steps = alpha, init_timestep, tmin, tmax, num_steps
+        self.kappa1, self.kappa2, self.kappa4 = cfg_train_fake, cfg_eval_fake, cfg_eval_real
+        self.loss_scaling, self.loss_scaling_G = loss_scaling, loss_scaling_G
+        self.ema_halflife_kimg, self.ema_rampup_ratio = ema_halflife_kimg, ema_rampup_ratio
+        self.cur_nimg = 0
+        true_score.eval().requires_grad_(False)
+        if G_ema is not None:
+            G_ema.eval().requires_grad_(False)
+        fake_score.flat.init_adam(betas[0])
+        G.flat.init_adam(betas[0])
+
+    # -- f_psi update: sid_training_loop.py:389-462 --------------------------------------------------------
+    def fake_score_phase(self, microbatches, batch_gpu_total=None):
+        """microbatches: list of dicts {z, noise, t, cond, uncond[, sub_noise]} (device tensors)."""
+        G, f = self.G, self.fake_score
+        f.train().requires_grad_(True)
+        f.flat.zero_grad()
+        total = batch_gpu_total or sum(m["z"].shape[0] for m in microbatches)
+        out = None
+        for m in microbatches:
+            b = m["z"].shape[0]
+            prompts = PromptBatch(m["cond"], m["uncond"])
+            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=m["z"].device)
+            with torch.no_grad():
+                images = sid_sd_sampler(G, m["z"], prompts, init_t, self.sched, num_steps=self.num_steps,
+                                        sub_noise=m.get("sub_noise"))
+            eps_hat = sid_sd_denoise(f, images, m["noise"], prompts, m["t"], self.sched, predict_x0=False,
+                                     guidance_scale=self.kappa1)
+            loss, out = ops.fake_loss(eps_hat, m["noise"], self.loss_scaling / total)
+            loss.backward()
+        f.eval().requires_grad_(False)
+        f.flat.allreduce_grad()
+        f.flat.adam_step(self.lr, self.betas, self.eps, grad_scale=1.0 / _world())
+        return out  # device float[2] {loss of the last micro-batch, valid rows}: no host sync here
+
+    # -- G_theta update: sid_training_loop.py:468-549, EMA :553-565 -----------------------------------------
+    def generator_phase(self, microbatches, batch_gpu_total=None, batch_size=None, return_images=False):
+        G, f, phi = self.G, self.fake_score, self.true_score
+        G.train().requires_grad_(True)
+        G.flat.zero_grad()
+        total = batch_gpu_total or sum(m["z"].shape[0] for m in microbatches)
+        out = None
+        imgs = []
+        for m in microbatches:
+            b = m["z"].shape[0]
+            prompts = PromptBatch(m["cond"], m["uncond"])
+            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=m["z"].device)
+            images = sid_sd_sampler(G, m["z"], prompts, init_t, self.sched, num_steps=self.num_steps,
+                                    sub_noise=m.get("sub_noise"))
+            y_fake = sid_sd_denoise(f, images, m["noise"], prompts, m["t"], self.sched, guidance_scale=self.kappa2)
+            y_real = sid_sd_denoise(phi, images, m["noise"], prompts, m["t"], self.sched, guidance_scale=self.kappa4)
+            loss, out = ops.lsg_loss(images, y_real, y_fake, self.alpha, self.loss_scaling_G / total)
+            loss.backward()
+            if return_images:
+                imgs.append(images.detach())
+        G.eval().requires_grad_(False)
+        G.flat.allreduce_grad()
+        world = _world()
+        bs = batch_size or total * world
+        beta = 0.0
+        ema = None
+        if self.G_ema is not None and self.ema_halflife_kimg > 0:
+            beta = ema_beta(bs, self.cur_nimg, self.ema_halflife_kimg, self.ema_rampup_ratio)
+            ema = self.G_ema.flat
+        G.flat.adam_step(self.glr, self.betas, self.eps, grad_scale=1.0 / world, clip=1.0 if self.fp16 else 0.0,
+                         ema=ema, ema_beta=beta)
+        self.cur_nimg += bs
+        if return_images:
+            return out, torch.cat(imgs)
+        return out
+
+    def iteration(self, mb_f, mb_g, batch_size=None):
+        lf = self.fake_score_phase(mb_f)
+        lg = self.generator_phase(mb_g, batch_size=batch_size)
+        return lf, lg
+
+
+def synth_microbatch(b, cfg, seed, device, dropout=False, num_steps=1, tmin=20, tmax=980, pinned=False):
+    """Synthetic inputs of SURVEY.md §8d, drawn on the HOST with the same generator recipe as the oracle's
+    synth_microbatch (so the CUDA path and the CPU oracle see identical numbers), then copied to `device`."""
+    g = torch.Generator().manual_seed(seed)
+    hw, d = cfg.sample_size, cfg.cross_attention_dim
+    ug = torch.Generator().manual_seed(1234567)
+    uncond1 = torch.randn([1, 77, d], generator=ug)
+    cond = torch.randn([b, 77, d], generator=g)
+    uncond = uncond1.expand(b, 77, d).contiguous()
+    if dropout:
+        drop = torch.rand(b, generator=g) < 0.1
+        cond = torch.where(drop[:, None, None], uncond, cond)
+    m = dict(cond=cond, uncond=uncond,
+             z=torch.randn([b, cfg.in_channels, hw, hw], generator=g),
+             noise=torch.randn([b, cfg.in_channels, hw, hw], generator=g),
+             t=torch.randint(tmin, tmax, (b,), generator=g, dtype=torch.long))
+    if num_steps > 1:
+        m["sub_noise"] = [torch.randn([b, cfg.in_channels, hw, hw], generator=g) for _ in range(num_steps - 1)]
+    if pinned:
+        m = {k: ([x.pin_memory() for x in v] if isinstance(v, list) else v.pin_memory()) for k, v in m.items()}
+    if device is None:
+        return m
+    return to_device(m, device)
+
+
+def to_device(m, device):
+    return {k: ([x.to(device, non_blocking=True) for x in v] if isinstance(v, list) else v.to(device, non_blocking=True))
+            for k, v in m.items()}
