@@ -34,6 +34,8 @@ extern "C" {
 const char* sidlsg_last_error();
 int sidlsg_version();
 int sidlsg_device_arch(int device);
+/* diagnostics: out (HOST memory) long[2] = {tcgen05 GEMM/conv launches, CUDA-core GEMM/conv launches} */
+int sidlsg_counters(long* out);
 
 /* ---- dense contractions --------------------------------------------------------------------------------
  * C[z][m][n] = alpha * sum_k A[z][m][k] B[z][k][n] (+ bias[n]) (+ rowvec[m / rows_per_vec][n]) (+ res[z][m][n])

@@ -28,4 +28,8 @@ for bwd in (False, True):
     ev0.record(); y = run(bwd); ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     fl = 0.8033e12 * b * (3 if bwd else 1)
+    import ctypes
+    cnt = (ctypes.c_long * 2)()
+    S.lib.call("counters", ctypes.addressof(cnt))
+    print("tc launches %d simt launches %d" % (cnt[0], cnt[1]))
     print("b=%d %s %s: %.1f ms  %.1f TFLOP/s  calls %d  finite %s  mem %.1f GB" % (b, dtype, "fwd+bwd" if bwd else "fwd", ms, fl / ms / 1e9, S.lib.launches - n0, bool(torch.isfinite(y).all()), torch.cuda.max_memory_allocated() / 1e9))

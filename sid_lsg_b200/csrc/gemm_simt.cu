@@ -206,10 +206,13 @@ gemm_core(LA la, LB lb, Epilogue<TO> epi, int M, int N, int K, int ksplit, int a
     for (int j = 0; j < TN; ++j) epi.store(z, m0 + ty + 16 * i, n0 + tx + 16 * j, acc[i][j], split == 0);
 }
 
+long g_simt_launches = 0;
+
 template <class LA, class LB, class TO>
 static int launch_core(LA la, LB lb, Epilogue<TO> epi, int M, int N, int K, int nbatch, int ksplit,
                        int a_kc, int b_kc, cudaStream_t st) {
   if (M <= 0 || N <= 0 || nbatch <= 0) return SIDLSG_OK;
+  __atomic_add_fetch(&g_simt_launches, 1, __ATOMIC_RELAXED);
   bool big = (long)M * N >= 128L * 128 * 64 && M >= 128 && N >= 96;
   if (big) {
     dim3 grid(cdiv(N, 128), cdiv(M, 128), nbatch * ksplit);
@@ -232,6 +235,17 @@ static int pick_ksplit(int M, int N, int K, int nbatch) {
   return (int)s;
 }
 
+// tensor-core (tcgen05) paths of gemm_tc.cu: return 1 = handled, 0 = shape not eligible, <0 = error
+int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, long b_sk, void* c, long ldc,
+                const float* bias, const void* res, long ldr, const float* rowvec, int rows_per_vec, float alpha,
+                int accumulate, int M, int N, int K, int in_dtype, int out_dtype, cudaStream_t st);
+int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec,
+                   int B, int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride,
+                   int up, int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st);
+int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
+                         int Cout, long dw_sco, long dw_stap, long dw_sci, int stride, int up, int accumulate,
+                         int in_dtype, cudaStream_t st);
+
 }  // namespace sidlsg
 
 using namespace sidlsg;
@@ -245,6 +259,11 @@ extern "C" int sidlsg_gemm(const void* a, long a_sm, long a_sk, long a_sb1, long
   if (M < 0 || N < 0 || K < 0 || nb1 < 1 || nb2 < 1) { set_error("sidlsg_gemm: bad shape"); return SIDLSG_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   int nbatch = nb1 * nb2;
+  if (nbatch == 1 && M > 0 && N > 0 && K > 0) {
+    int r = tc_gemm_try(a, a_sm, a_sk, b, b_sn, b_sk, c, ldc, bias, res, ldr, rowvec, rows_per_vec, alpha, accumulate,
+                        M, N, K, in_dtype, out_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
+  }
   int ksplit = 1;
   if (accumulate == 2) {
     if (out_dtype != SIDLSG_F32) { set_error("sidlsg_gemm: atomic accumulate needs fp32 output"); return SIDLSG_ERR_ARG; }
@@ -276,6 +295,11 @@ extern "C" int sidlsg_conv3x3(const void* x, const void* w, void* y, const float
     set_error("sidlsg_conv3x3: bad shape"); return SIDLSG_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0) {
+    int r = tc_conv3x3_try(x, w, y, bias, res, rowvec, B, Hi, Wi, Kc, Ho, Wo, N, w_sn, w_stap, w_sk, stride, up,
+                           transposed, flip, accumulate, in_dtype, out_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
+  }
   int M = B * Ho * Wo, K = 9 * Kc;
   ConvGeom g{B, Hi, Wi, Kc, Ho, Wo, stride, up, transposed};
 #define RUN(TI, TO_)                                                                                      \
@@ -299,6 +323,11 @@ extern "C" int sidlsg_conv3x3_wgrad(const void* x, const void* dy, float* dw, in
                                     int Ho, int Wo, int Cout, long dw_sco, long dw_stap, long dw_sci,
                                     int stride, int up, int accumulate, int in_dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0) {
+    int r = tc_conv3x3_wgrad_try(x, dy, dw, B, Hi, Wi, Cin, Ho, Wo, Cout, dw_sco, dw_stap, dw_sci, stride, up,
+                                 accumulate, in_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
+  }
   int M = Cout, N = 9 * Cin, K = B * Ho * Wo;
   ConvGeom g{B, Hi, Wi, Cin, Ho, Wo, stride, up, 0};
   int ksplit = pick_ksplit(M, N, K, 1);

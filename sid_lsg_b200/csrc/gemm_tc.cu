@@ -1,0 +1,679 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM conv3x3 for the bf16 mode of the SiD-LSG step (sm_100a only).
+//
+// One persistent, warp-specialised kernel covers every dense contraction of the UNet forward/backward:
+//   linear fwd      C[M,N]   = A[M,K]  W[N,K]^T          A K-major,   B K-major
+//   linear dgrad    dX[M,K]  = dY[M,N] W[N,K]            A K-major,   B MN-major (2-D map over W)
+//   linear wgrad    dW[N,K] += dY[M,N]^T X[M,K]          A MN-major,  B MN-major, split-K + fp32 red.add
+//   conv3x3 fwd     NHWC implicit GEMM: A = 4-D TMA boxes of x shifted per tap (zero padding = TMA OOB fill),
+//                   B = weights [Cout][tap][Cin] K-major
+//   conv3x3 dgrad   A = 4-D boxes of dY shifted by -tap, B = 3-D map (Cin, tap, Cout) MN-major
+//   conv3x3 wgrad   A = dY MN-major, B = 4-D boxes of x shifted per tap (MN-major), one tap per N tile, split-K
+// (reference call sites: every Conv2d / Linear of the UNet behind training/sid_sd_util.py:184,245,263 and their
+// autograd, training/sid_training_loop.py:450,533).
+//
+// Roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias / timestep-row / residual -> global).
+// 4-stage smem ring (128x64 A + up to 256x64 B, SWIZZLE_128B), two 256-column fp32 accumulators in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Tiles are 128 x block_n with a narrower last N tile
+// (UMMA N is a run-time field of the instruction descriptor), so N = 320 = 192 + 128 wastes nothing.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace sidlsg {
+
+enum { A_K2D = 0, A_MN2D = 1, A_CONV = 2 };
+enum { B_K2D = 0, B_MN2D = 1, B_W3D = 2, B_CONV = 3 };
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
+constexpr int TC_B_BYTES = 256 * TC_BK * 2;          // 32 KB (max block_n)
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 256;
+
+struct TcParams {
+  int M, N;                 // output extent (rows, columns of the logical GEMM)
+  int block_n;              // N tile (multiple of 16; multiple of 64 for MN-major B)
+  int m_tiles, n_tiles, splits;
+  int kb_total;             // 64-deep reduction blocks
+  int a_mode, b_mode;
+  // convolution geometry (A_CONV / B_CONV / B_W3D)
+  int H, W;                 // image extent of the tensor the boxes are cut from
+  int cchunks;              // 64-channel chunks per tap in the reduction (conv fwd / dgrad)
+  int flip;                 // dgrad: sample at -tap offset
+  int n_tiles_per_tap;      // conv wgrad: N tiles per tap
+  int cin;                  // conv wgrad: channels per tap (column offset = tap*cin + n_in)
+  // epilogue
+  void* c;
+  long ldc;
+  int out_f32;
+  const float* bias;
+  const void* res;          // same dtype as c
+  long ldr;
+  const float* rowvec;
+  int rows_per_vec;
+  float alpha;
+  int atomic;               // fp32 red.add (split-K / gradient accumulation)
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (long it = 0; it < (1L << 26); ++it) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  printf("sidlsg gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // C format fp32
+  d |= 1u << 7;                      // A format bf16
+  d |= 1u << 10;                     // B format bf16
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(TC_BM >> 4) << 24;
+  return d;
+}
+
+struct TileInfo {
+  int m0, n_in, col0, n_valid, tap, kb0, kb1;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
+  TileInfo t;
+  int split = tile % p.splits;
+  int r = tile / p.splits;
+  int n_blk = r % p.n_tiles;
+  int m_blk = r / p.n_tiles;
+  t.m0 = m_blk * TC_BM;
+  if (p.b_mode == B_CONV) {
+    t.tap = n_blk / p.n_tiles_per_tap;
+    t.n_in = (n_blk - t.tap * p.n_tiles_per_tap) * p.block_n;
+    t.col0 = t.tap * p.cin + t.n_in;
+    t.n_valid = min(p.block_n, p.cin - t.n_in);
+  } else {
+    t.tap = 0;
+    t.n_in = n_blk * p.block_n;
+    t.col0 = t.n_in;
+    t.n_valid = min(p.block_n, p.N - t.n_in);
+  }
+  int per = (p.kb_total + p.splits - 1) / p.splits;
+  t.kb0 = split * per;
+  t.kb1 = min(p.kb_total, t.kb0 + per);
+  return t;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-B alignment
+  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int a_mn = p.a_mode == A_MN2D;
+  const int b_mn = p.b_mode != B_K2D;
+  const int b_boxes = (p.block_n + 63) >> 6;
+  const uint32_t stage_tx = TC_A_BYTES + (b_mn ? b_boxes * 8192 : p.block_n * 128);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.H * p.W;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        int ab0 = 0, ah0 = 0;
+        if (p.a_mode == A_CONV) { ab0 = t.m0 / hw; ah0 = (t.m0 - ab0 * hw) / p.W; }
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, stage_tx);
+          int tap = 0, c0 = kb * TC_BK;
+          if (p.a_mode == A_CONV || p.b_mode == B_W3D) { tap = kb / p.cchunks; c0 = (kb - tap * p.cchunks) * TC_BK; }
+          // ---- A ----
+          if (p.a_mode == A_K2D) {
+            tma_load_2d(&tmA, fb, sa, kb * TC_BK, t.m0);
+          } else if (p.a_mode == A_MN2D) {
+            tma_load_2d(&tmA, fb, sa, t.m0, kb * TC_BK);
+            tma_load_2d(&tmA, fb, sa + 8192, t.m0 + 64, kb * TC_BK);
+          } else {
+            int oy = tap / 3 - 1, ox = tap % 3 - 1;
+            if (p.flip) { oy = -oy; ox = -ox; }
+            tma_load_4d(&tmA, fb, sa, c0, ox, ah0 + oy, ab0);
+          }
+          // ---- B ----
+          if (p.b_mode == B_K2D) {
+            tma_load_2d(&tmB, fb, sb, kb * TC_BK, t.n_in);
+          } else if (p.b_mode == B_MN2D) {
+            for (int j = 0; j < b_boxes; ++j) tma_load_2d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, kb * TC_BK);
+          } else if (p.b_mode == B_W3D) {
+            for (int j = 0; j < b_boxes; ++j) tma_load_3d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, tap, c0);
+          } else {  // B_CONV: reduction block = 64 pixels starting at kb*64
+            const int pix0 = kb * TC_BK;
+            const int bb0 = pix0 / hw;
+            const int bh0 = (pix0 - bb0 * hw) / p.W;
+            const int oy = t.tap / 3 - 1, ox = t.tap % 3 - 1;
+            for (int j = 0; j < b_boxes; ++j) tma_load_4d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, ox, bh0 + oy, bb0);
+          }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase[2] = {0, 0};
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        const int n_mma = b_mn ? ((t.n_valid + 63) & ~63) : ((t.n_valid + 15) & ~15);
+        const uint32_t idesc = make_idesc(n_mma, a_mn, b_mn);
+        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ad = a_mn ? make_desc(sa + k * 2048, 1024, 8192) : make_desc(sa + k * 32, 1024, 0);
+            const uint64_t bd = b_mn ? make_desc(sb + k * 2048, 1024, 8192) : make_desc(sb + k * 32, 1024, 0);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+          tc_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(p, tile);
+      mbar_wait(tfull_bar(acc), acc_phase[acc]);
+      tc_fence_after();
+      const int m = t.m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const bool has_work = t.kb1 > t.kb0;
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const long crow = (long)m * p.ldc + t.col0;
+      const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long)(m / p.rows_per_vec) * p.N + t.col0 : nullptr;
+      for (int c = 0; c < t.n_valid; c += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(taddr + c, v);          // warp-collective: every lane participates, stores are predicated
+        if (row_ok && has_work) {
+        const int nc = min(16, t.n_valid - c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i < nc) v[i] += __ldg(p.bias + t.col0 + c + i);
+        }
+        if (rv) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i < nc) v[i] += __ldg(rv + c + i);
+        }
+        if (p.out_f32) {
+          float* cp = reinterpret_cast<float*>(p.c) + crow + c;
+          if (p.res) {
+            const float* rp = reinterpret_cast<const float*>(p.res) + (long)m * p.ldr + t.col0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < nc) v[i] += rp[i];
+          }
+          if (p.atomic) {
+            if (nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+            } else {
+              for (int i = 0; i < nc; ++i) atomicAdd(cp + i, v[i]);
+            }
+          } else if (nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < nc; ++i) cp[i] = v[i];
+          }
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(p.c) + crow + c;
+          const bool vec = nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
+          if (p.res) {
+            const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (long)m * p.ldr + t.col0 + c;
+            if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+              uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
+              const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
+              const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[i] += __bfloat162float(e0[i]); v[8 + i] += __bfloat162float(e1[i]); }
+            } else {
+              for (int i = 0; i < nc; ++i) v[i] += __bfloat162float(rp[i]);
+            }
+          }
+          if (vec) {
+            uint4 o0, o1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+            }
+            *reinterpret_cast<uint4*>(cp) = o0;
+            *reinterpret_cast<uint4*>(cp + 8) = o1;
+          } else {
+            for (int i = 0; i < nc; ++i) cp[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, inner box 64 elements.  dims/strides innermost first; strides[i] (bytes) for dim i+1.
+static bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT && r != CUDA_ERROR_NOT_INITIALIZED) break;
+    // this thread (e.g. an autograd engine thread) has no current context for THIS runtime instance yet:
+    // a runtime call binds the device's primary context, then retry once
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu box %u,%u stride0 %llu base %p", (int)r, rank,
+              (unsigned long long)gd[0], (unsigned long long)gd[1], bx[0], bx[1], (unsigned long long)gs[0], base);
+    return false;
+  }
+  return true;
+}
+
+static int g_tc_state = -1;   // -1 unknown, 0 off, 1 on
+static int g_num_sms = 148;
+
+bool tc_enabled() {
+  if (g_tc_state < 0) {
+    const char* e = getenv("SIDLSG_DISABLE_TC");
+    int dev = 0;
+    cudaDeviceProp prop;
+    bool ok = !(e && e[0] == '1') && cudaGetDevice(&dev) == cudaSuccess &&
+              cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10 && get_encode() != nullptr;
+    if (ok) {
+      g_num_sms = prop.multiProcessorCount;
+      ok = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+    }
+    cudaGetLastError();
+    g_tc_state = ok ? 1 : 0;
+  }
+  return g_tc_state == 1;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int pick_block_n(int n, bool mn_major) {
+  // largest tile <= 256 that leaves the least padded work; MN-major tiles come in 64-column TMA boxes
+  int step = mn_major ? 64 : 16;
+  int best = step, best_cost = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    int tiles = (n + bn - 1) / bn;
+    int last = n - (tiles - 1) * bn;
+    int last_pad = (last + step - 1) / step * step;
+    int cost = (tiles - 1) * bn + last_pad;          // columns actually multiplied
+    cost += tiles * 8;                               // mild preference for fewer, wider tiles
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+long g_tc_launches = 0;
+extern long g_simt_launches;
+
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+  long tiles = (long)p.m_tiles * p.n_tiles * p.splits;
+  if (tiles <= 0) return SIDLSG_OK;
+  __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
+  int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
+  return check_launch("gemm_tc");
+}
+
+static int pick_splits(long tiles, int kb_total) {
+  if (tiles >= g_num_sms) return 1;
+  long s = (2L * g_num_sms + tiles - 1) / tiles;
+  long maxs = kb_total / 8;   // at least 8 k-blocks (512 reduction elements) per split
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  if (s > 128) s = 128;
+  return (int)s;
+}
+
+// Returns 1 if handled on the tensor cores, 0 if the shape is not eligible (caller falls back to the CUDA-core
+// kernel of gemm_simt.cu, which is the same arithmetic), <0 on error.
+int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, long b_sk, void* c, long ldc,
+                const float* bias, const void* res, long ldr, const float* rowvec, int rows_per_vec, float alpha,
+                int accumulate, int M, int N, int K, int in_dtype, int out_dtype, cudaStream_t st) {
+  if (!tc_enabled() || in_dtype != SIDLSG_BF16) return 0;
+  if (M < 64 || N < 16 || K < 64 || (N % 8)) return 0;
+  if (accumulate == 1) return 0;
+  if (accumulate == 2 && out_dtype != SIDLSG_F32) return 0;
+  const bool a_k = a_sk == 1, a_mn = a_sm == 1 && !a_k;
+  const bool b_k = b_sk == 1, b_mn = b_sn == 1 && !b_k;
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return 0;
+  const long lda = a_k ? a_sm : a_sk, ldb = b_k ? b_sn : b_sk;
+  if ((lda % 8) || (ldb % 8) || !aligned16(a) || !aligned16(b)) return 0;
+  if (a_mn && (M % 8)) return 0;
+  if (b_mn && (N % 8)) return 0;
+  if (out_dtype == SIDLSG_BF16 && (ldc % 8)) return 0;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.block_n = pick_block_n(N, b_mn);
+  p.m_tiles = (M + TC_BM - 1) / TC_BM;
+  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  p.kb_total = (K + TC_BK - 1) / TC_BK;
+  p.splits = accumulate == 2 ? pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total) : 1;
+  p.a_mode = a_k ? A_K2D : A_MN2D;
+  p.b_mode = b_k ? B_K2D : B_MN2D;
+  p.c = c; p.ldc = ldc; p.out_f32 = out_dtype == SIDLSG_F32;
+  p.bias = bias; p.res = res; p.ldr = ldr; p.rowvec = rowvec; p.rows_per_vec = rows_per_vec > 0 ? rows_per_vec : 1;
+  p.alpha = alpha; p.atomic = accumulate == 2;
+
+  CUtensorMap ta, tb;
+  if (a_k) {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
+    uint32_t bx[2] = {64, 128};
+    if (!make_map(&ta, a, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  } else {
+    uint64_t d[2] = {(uint64_t)M, (uint64_t)K}, s[1] = {(uint64_t)lda * 2};
+    uint32_t bx[2] = {64, 64};
+    if (!make_map(&ta, a, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  if (b_k) {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
+    uint32_t bx[2] = {64, (uint32_t)p.block_n};
+    if (!make_map(&tb, b, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  } else {
+    uint64_t d[2] = {(uint64_t)N, (uint64_t)K}, s[1] = {(uint64_t)ldb * 2};
+    uint32_t bx[2] = {64, 64};
+    if (!make_map(&tb, b, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  int r = launch_tc(ta, tb, p, st);
+  return r == SIDLSG_OK ? 1 : r;
+}
+
+// tile geometry for cutting 128 (or 64) consecutive pixels out of [B, H, W, C]: whole image rows only
+static bool conv_box(int H, int W, int pixels, uint32_t* wt, uint32_t* ht, uint32_t* nt) {
+  if (W > pixels || (pixels % W)) return false;
+  int rows = pixels / W;
+  if (rows <= H) {
+    if (H % rows) return false;
+    *wt = W; *ht = rows; *nt = 1;
+  } else {
+    if (rows % H) return false;
+    *wt = W; *ht = H; *nt = rows / H;
+  }
+  return *wt <= 256 && *ht <= 256 && *nt <= 256;
+}
+
+// conv3x3 stride 1: forward (flip=0, weights [N][tap][Kc]) or data gradient (flip=1, x := dy, weights [Kc][tap][N])
+int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec,
+                   int B, int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride,
+                   int up, int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st) {
+  if (!tc_enabled() || in_dtype != SIDLSG_BF16 || out_dtype != SIDLSG_BF16) return 0;
+  if (stride != 1 || up != 1 || transposed || accumulate) return 0;
+  if (Hi != Ho || Wi != Wo || (Kc % 64) || (N % 8) || !aligned16(x) || !aligned16(w)) return 0;
+  const bool fwd = !flip && w_sk == 1 && w_stap == Kc && w_sn == 9L * Kc;
+  const bool dgrad = flip && w_sn == 1 && w_stap == N && w_sk == 9L * N;
+  if (!fwd && !dgrad) return 0;
+  if (dgrad && (N % 64)) return 0;
+  uint32_t wt, ht, nt;
+  if (!conv_box(Hi, Wi, 128, &wt, &ht, &nt)) return 0;
+  const long M = (long)B * Hi * Wi;
+  if (M < 128) return 0;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N;
+  p.block_n = pick_block_n(N, dgrad);
+  p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  p.splits = 1;
+  p.cchunks = Kc / 64;
+  p.kb_total = 9 * p.cchunks;
+  p.a_mode = A_CONV;
+  p.b_mode = fwd ? B_K2D : B_W3D;
+  p.H = Hi; p.W = Wi; p.flip = flip;
+  p.c = y; p.ldc = N; p.out_f32 = 0;
+  p.bias = bias; p.res = res; p.ldr = N; p.rowvec = rowvec; p.rows_per_vec = Ho * Wo; p.alpha = 1.f;
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[4] = {(uint64_t)Kc, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)Kc * 2, (uint64_t)Wi * Kc * 2, (uint64_t)Hi * Wi * Kc * 2};
+    uint32_t bx[4] = {64, wt, ht, nt};
+    if (!make_map(&ta, x, 4, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  if (fwd) {
+    uint64_t d[2] = {(uint64_t)9 * Kc, (uint64_t)N}, s[1] = {(uint64_t)9 * Kc * 2};
+    uint32_t bx[2] = {64, (uint32_t)p.block_n};
+    if (!make_map(&tb, w, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  } else {
+    // weights physically [Kc = cout][tap][N = cin]: dims (cin, tap, cout)
+    uint64_t d[3] = {(uint64_t)N, 9, (uint64_t)Kc}, s[2] = {(uint64_t)N * 2, (uint64_t)9 * N * 2};
+    uint32_t bx[3] = {64, 1, 64};
+    if (!make_map(&tb, w, 3, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  int r = launch_tc(ta, tb, p, st);
+  return r == SIDLSG_OK ? 1 : r;
+}
+
+// dw[co][tap][ci] += sum_pix dy[pix][co] * window(x)[pix][tap][ci]   (stride 1; dw fp32 dense [Cout][9][Cin])
+int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
+                         int Cout, long dw_sco, long dw_stap, long dw_sci, int stride, int up, int accumulate,
+                         int in_dtype, cudaStream_t st) {
+  if (!tc_enabled() || in_dtype != SIDLSG_BF16) return 0;
+  if (stride != 1 || up != 1 || Hi != Ho || Wi != Wo) return 0;
+  if ((Cin % 64) || (Cout % 8) || Cout < 64 || !aligned16(x) || !aligned16(dy) || !aligned16(dw)) return 0;
+  if (!(dw_sci == 1 && dw_stap == Cin && dw_sco == 9L * Cin)) return 0;
+  uint32_t wt, ht, nt;
+  if (!conv_box(Hi, Wi, 64, &wt, &ht, &nt)) return 0;
+  const long npix = (long)B * Hi * Wi;
+  if (npix < 64 || (npix % 64)) return 0;
+  if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * 9 * Cin, st);
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = Cout; p.N = 9 * Cin;
+  p.block_n = pick_block_n(Cin, true);
+  p.m_tiles = (Cout + TC_BM - 1) / TC_BM;
+  p.n_tiles_per_tap = (Cin + p.block_n - 1) / p.block_n;
+  p.n_tiles = 9 * p.n_tiles_per_tap;
+  p.cin = Cin;
+  p.kb_total = (int)(npix / 64);
+  p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
+  p.a_mode = A_MN2D;
+  p.b_mode = B_CONV;
+  p.H = Hi; p.W = Wi;
+  p.c = dw; p.ldc = 9L * Cin; p.out_f32 = 1; p.alpha = 1.f; p.atomic = 1; p.rows_per_vec = 1;
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[2] = {(uint64_t)Cout, (uint64_t)npix}, s[1] = {(uint64_t)Cout * 2};
+    uint32_t bx[2] = {64, 64};
+    if (!make_map(&ta, dy, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  {
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Wi * Cin * 2, (uint64_t)Hi * Wi * Cin * 2};
+    uint32_t bx[4] = {64, wt, ht, nt};
+    if (!make_map(&tb, x, 4, d, s, bx)) return SIDLSG_ERR_CUDA;
+  }
+  int r = launch_tc(ta, tb, p, st);
+  return r == SIDLSG_OK ? 1 : r;
+}
+
+}  // namespace sidlsg
+
+// diagnostics: out[0] = tcgen05 GEMM/conv launches, out[1] = CUDA-core GEMM/conv launches (host memory)
+extern "C" int sidlsg_counters(long* out) {
+  out[0] = sidlsg::g_tc_launches;
+  out[1] = sidlsg::g_simt_launches;
+  return SIDLSG_OK;
+}

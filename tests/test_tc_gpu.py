@@ -1,0 +1,112 @@
+"""tcgen05 tensor-core paths (gemm_tc.cu) through the C ABI vs fp32 PyTorch on bf16-rounded inputs.
+
+Inputs are rounded to bf16 first, so the only differences are fp32 accumulation order and the bf16 rounding of
+the outputs: tolerance 1.5e-2 relative to the output scale for bf16 outputs, 2e-3 for fp32 (wgrad) outputs.
+Shapes are chosen to satisfy the tensor-core eligibility rules (channels % 64 == 0, >= 128 pixels ...).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ops():
+    from sid_lsg_b200 import ops as o
+    return o
+
+
+def bf(t):
+    return t.bfloat16().float()
+
+
+def check(a, b, tol, what):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    scale = b.abs().max().item() + 1e-12
+    err = (a - b).abs().max().item() / scale
+    rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+    assert err < tol * 4 and rel < tol, "%s: max err/scale %g, rel L2 %g" % (what, err, rel)
+
+
+class BfParam:
+    """fp32 master Parameter with a bf16 shadow and a zeroed fp32 grad, like params.FlatParams produces."""
+
+    def __new__(cls, t, channels_last=False):
+        t = bf(t).to(DEV)
+        if channels_last:
+            t = t.contiguous(memory_format=torch.channels_last)
+        p = torch.nn.Parameter(t)
+        p.grad = torch.zeros_like(p)
+        p._shadow = p.detach().to(torch.bfloat16)  # preserves the physical layout
+        return p
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 64, 64), (4096, 320, 320), (1000, 768, 640), (512, 1280, 2560), (300, 640, 136),
+                                   (8192, 320, 960)])
+def test_tc_linear(M, K, N):
+    g = torch.Generator().manual_seed(0)
+    x = bf(torch.randn(M, K, generator=g))
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    r = bf(torch.randn(M, N, generator=g))
+    dy = bf(torch.randn(M, N, generator=g))
+    xr, wr, br, rr = (t.clone().requires_grad_(True) for t in (x, w, b, r))
+    yr = F.linear(xr, wr, br) + rr
+    yr.backward(dy)
+    xd = x.to(DEV).bfloat16().requires_grad_(True)
+    rd = r.to(DEV).bfloat16().requires_grad_(True)
+    wp = BfParam(w)
+    bp = torch.nn.Parameter(b.to(DEV))
+    bp.grad = torch.zeros_like(bp)
+    y = ops().linear(xd, wp, bp, rd)
+    y.backward(dy.to(DEV).bfloat16())
+    check(y, yr, 1.5e-2, "y")
+    check(xd.grad, xr.grad, 1.5e-2, "dx")
+    check(wp.grad, wr.grad, 2e-3, "dw")
+    check(bp.grad, br.grad, 2e-3, "db")
+
+
+@pytest.mark.parametrize("B,H,C,N", [(2, 16, 64, 64), (1, 64, 64, 128), (3, 32, 128, 64), (4, 8, 320, 320),
+                                     (2, 16, 192, 320), (1, 64, 320, 320), (5, 8, 64, 192)])
+def test_tc_conv3x3(B, H, C, N):
+    g = torch.Generator().manual_seed(1)
+    x = bf(torch.randn(B, C, H, H, generator=g))
+    w = bf(torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    b = torch.randn(N, generator=g)
+    rv = torch.randn(B, N, generator=g)
+    res = bf(torch.randn(B, N, H, H, generator=g))
+    xr, wr, br, rvr = (t.clone().requires_grad_(True) for t in (x, w, b, rv))
+    yr = F.conv2d(xr, wr, br, padding=1) + rvr[:, :, None, None] + res
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16().requires_grad_(True)
+    rvd = rv.to(DEV).requires_grad_(True)
+    wp = BfParam(w, channels_last=True)
+    bp = torch.nn.Parameter(b.to(DEV))
+    bp.grad = torch.zeros_like(bp)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+    y = ops().conv3x3(xd, wp, bp, resd, rvd)
+    y.backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
+    check(y.permute(0, 3, 1, 2), yr, 1.5e-2, "y")
+    check(xd.grad.permute(0, 3, 1, 2), xr.grad, 1.5e-2, "dx")
+    check(wp.grad, wr.grad, 2e-3, "dw")
+    check(rvd.grad, rvr.grad, 1e-2, "drowvec")
+
+
+def test_tc_wgrad_accumulates():
+    """two backward passes (gradient accumulation rounds) add up in the fp32 grad bucket."""
+    g = torch.Generator().manual_seed(2)
+    x = bf(torch.randn(2, 64, 16, 16, generator=g))
+    w = bf(torch.randn(64, 64, 3, 3, generator=g) / 24)
+    wr = w.clone().requires_grad_(True)
+    wp = BfParam(w, channels_last=True)
+    for _ in range(2):
+        dy = bf(torch.randn(2, 64, 16, 16, generator=g))
+        F.conv2d(x, wr, None, padding=1).backward(dy)
+        xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
+        ops().conv3x3(xd, wp).backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
+    check(wp.grad, wr.grad, 2e-3, "dw accumulated")
