@@ -93,6 +93,14 @@ int sidlsg_softmax_fwd(const float* S, void* P, long rows, int cols, float scale
 int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int cols, float scale, int dtype,
                        void* stream);
 
+/* Flash attention on tcgen05/TMEM/TMA (bf16): o = softmax(q k^T / sqrt(d)) v per (batch, head) with no score
+ * matrix in HBM.  q [B,N,H*d], k/v [B,M,H*d], o [B,N,H*d] bf16 contiguous, heads interleaved in the channel dim;
+ * lse [B,H,N] fp32 = log-sum-exp of the scaled scores (kept for the backward; may be null).  d % 8 == 0,
+ * 16 <= d <= 192.  Returns SIDLSG_ERR_UNSUPPORTED if the device / shape cannot take the tensor-core path.
+ * ref: the attention call of every BasicTransformerBlock.attn1/attn2 (xformers / SDPA in the reference). */
+int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
+                         int M, int H, int d, void* stream);
+
 /* ---- elementwise ----------------------------------------------------------------------------------------- */
 /* UNet boundary: fp32 NCHW [B,C,HW] <-> token-major [B,HW,C] in the compute dtype (sample in, .sample out). */
 int sidlsg_nchw_to_nhwc(const float* x, void* y, int B, int C, int HW, int out_dtype, void* stream);

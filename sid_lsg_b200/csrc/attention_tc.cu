@@ -1,0 +1,287 @@
+// Flash attention on tcgen05 / TMEM / TMA (bf16 mode): softmax(Q K^T / sqrt(d)) V per (batch, head) without
+// materialising the scores.  Replaces diffusers' Attention (xformers memory_efficient_attention / SDPA,
+// /root/reference/training/sid_sd_util.py:102-113) for the self- and cross-attention of every
+// BasicTransformerBlock: (N, d) = (4096,40) (1024,80) (256,160) (64,160) for SD1.5, d = 64 for SD2.1, 77 text keys.
+//
+// One CTA = one 128-row query tile of one (batch, head); 192 threads:
+//   warps 0-3  softmax: one query row per thread; S is read from TMEM, P = exp2(s*c - m*c) is written as bf16 into
+//              a SWIZZLE_128B shared tile that feeds the second MMA; O stays in TMEM and is rescaled lazily (only
+//              when the running max grew by more than 2^8), so no per-tile O read-back
+//   warp 4     TMA producer: Q once, K/V tiles through a ring; head slices are cut with a 4-D tensor map
+//              (d, heads, tokens, batch), so the zero padding of d=40 -> 48/64 comes from TMA out-of-bounds fill
+//   warp 5     tcgen05.mma issuer + TMEM allocator: S = Q K^T (K-major x K-major), O += P V (V is the MN-major B)
+// Two CTAs fit per SM for d <= 64 so one CTA's exponentials overlap the other's MMAs (the d=40 layers are
+// MUFU-bound: 128x128 exps per tile vs ~400 tensor cycles).
+#include "tc_common.cuh"
+#include <string.h>
+
+namespace sidlsg {
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_BQ = 128;
+constexpr int AT_BKV = 128;
+constexpr int AT_CHUNK = 16384;   // [128 rows][64 bf16] SWIZZLE_128B
+
+struct AttnParams {
+  int B, H, N, M, d;
+  int dchunks, dpad, kv_stages;
+  float scale, scale_log2;
+  bf16* o;
+  float* lse;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int TCOLS>
+__global__ void __launch_bounds__(AT_THREADS, TCOLS == 256 ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const int ST = p.kv_stages;
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + p.dchunks * AT_CHUNK;
+  const uint32_t v_smem = k_smem + ST * p.dchunks * AT_CHUNK;
+  const uint32_t p_smem = v_smem + ST * p.dchunks * AT_CHUNK;
+  const uint32_t bar_base = p_smem + 2 * AT_CHUNK;
+  // barriers: q_full, s_full, p_full, o_full, k_full[2], v_full[2], kv_empty[2], then the TMEM slot
+  const uint32_t q_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24;
+  auto k_full = [&](int s) { return bar_base + 32 + 8u * s; };
+  auto v_full = [&](int s) { return bar_base + 48 + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 64 + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 80;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int T = (p.M + AT_BKV - 1) / AT_BKV;
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) { printf("sidlsg attention: dynamic smem not 1024-aligned\n"); __trap(); }
+    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(kv_empty(s), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 5) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 128;
+  const uint32_t tile_bytes = p.dchunks * AT_CHUNK;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, tile_bytes);
+      for (int c = 0; c < p.dchunks; ++c) tma_load_4d(&tmQ, q_full, q_smem + c * AT_CHUNK, c * 64, h, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % ST;
+        const uint32_t ph = (j / ST) & 1;
+        mbar_wait(kv_empty(st), ph ^ 1);
+        mbar_expect_tx(k_full(st), tile_bytes);
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(&tmK, k_full(st), k_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, j * AT_BKV, b);
+        mbar_expect_tx(v_full(st), tile_bytes);
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(&tmV, v_full(st), v_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, j * AT_BKV, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const int dsteps = p.dpad >> 4;
+      auto issue_qk = [&](int j) {
+        const int st = j % ST;
+        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+        const uint32_t idesc = make_idesc((n_valid + 15) & ~15, 0, 0);
+        const uint32_t kb = k_smem + st * tile_bytes;
+        for (int s = 0; s < dsteps; ++s) {
+          const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(s_tmem, make_desc(q_smem + off, 1024, 0), make_desc(kb + off, 1024, 0), idesc, s > 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      tc_fence_after();
+      issue_qk(0);
+      tc_commit(s_full);
+      const uint32_t idesc_pv = make_idesc(p.dpad, 0, 1);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % ST;
+        const uint32_t ph = (j / ST) & 1;
+        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full(st), ph);
+        tc_fence_after();
+        const uint32_t vb = v_smem + st * tile_bytes;
+        const int ksteps = (n_valid + 15) >> 4;
+        for (int s = 0; s < ksteps; ++s) {
+          tc_mma_bf16(o_tmem, make_desc(p_smem + (s >> 2) * AT_CHUNK + (s & 3) * 32, 1024, 0),
+                      make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, (j > 0 || s > 0) ? 1u : 0u);
+        }
+        tc_commit(kv_empty(st));
+        tc_commit(o_full);
+        if (j + 1 < T) {
+          const int st2 = (j + 1) % ST;
+          mbar_wait(k_full(st2), ((j + 1) / ST) & 1);
+          tc_fence_after();
+          issue_qk(j + 1);
+          tc_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / output (warps 0-3) =====================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float c = p.scale_log2;
+    float m_used = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int cc = 0; cc < n_valid; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (cc + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new - m_used) * c > 8.f;
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);   // P V of the previous tile retired: O and the P tile are ours again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+          for (int cc = 0; cc < p.dpad; cc += 16) {
+            uint32_t r[16];
+            tmem_ld16_nowait(o_tmem + lane_off + cc, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st16(o_tmem + lane_off + cc, r);
+          }
+          tmem_wait_st();
+          l_run *= f;
+        }
+      }
+      if (need) m_used = m_new;
+      const float mc = m_used * c;
+      for (int cc = 0; cc < n_valid; cc += 32) {
+        uint32_t r[32], pk[16];
+        tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (cc + i < n_valid) ? ex2f(fmaf(__uint_as_float(r[i]), c, -mc)) : 0.f;
+          float p1 = (cc + i + 1 < n_valid) ? ex2f(fmaf(__uint_as_float(r[i + 1]), c, -mc)) : 0.f;
+          l_run += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          st_shared_v4(p_smem + sw128_offset(row, cc + 8 * qd, AT_CHUNK), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                       pk[4 * qd + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (T - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + row;
+    const float inv = 1.f / l_run;
+    const int C = p.H * p.d;
+    bf16* orow = p.o + ((long)b * p.N + q) * C + h * p.d;
+    for (int cc = 0; cc < p.dpad; cc += 16) {
+      uint32_t r[16];
+      tmem_ld16_nowait(o_tmem + lane_off + cc, r);
+      tmem_wait_ld();
+      if (q < p.N) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (cc + 8 * hh < p.d) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[8 * hh + 0]) * inv, __uint_as_float(r[8 * hh + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(r[8 * hh + 2]) * inv, __uint_as_float(r[8 * hh + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(r[8 * hh + 4]) * inv, __uint_as_float(r[8 * hh + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(r[8 * hh + 6]) * inv, __uint_as_float(r[8 * hh + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + cc + 8 * hh) = o;
+          }
+        }
+      }
+    }
+    if (q < p.N && p.lse) p.lse[((long)b * p.H + h) * p.N + q] = m_used * p.scale + logf(l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int len, int B) {
+  const long C = (long)H * d;
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)len, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)C * 2, (uint64_t)len * C * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_map(m, base, 4, dims, strides, box);
+}
+
+static bool g_attn_attr_done = false;
+
+}  // namespace sidlsg
+
+using namespace sidlsg;
+
+// q [B,N,H*d], k/v [B,M,H*d] bf16 contiguous; o [B,N,H*d] bf16; lse [B,H,N] fp32 (natural log, may be null).
+// Returns SIDLSG_ERR_UNSUPPORTED when the tensor-core path cannot take the shape (caller uses the fp32-exact path).
+extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
+                                    int M, int H, int d, void* stream) {
+  if (!tc_enabled()) { set_error("attention_fwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
+  if (d % 8 || d < 16 || d > 192 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
+    set_error("attention_fwd: unsupported shape B=%d N=%d M=%d H=%d d=%d", B, N, M, H, d);
+    return SIDLSG_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.N = N; p.M = M; p.d = d;
+  p.dchunks = (d + 63) / 64;
+  p.dpad = (d + 15) & ~15;
+  p.kv_stages = p.dchunks <= 2 ? 2 : 1;
+  p.scale = 1.f / sqrtf((float)d);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.o = (bf16*)o; p.lse = lse;
+  CUtensorMap tq, tk, tv;
+  if (!make_head_map(&tq, q, d, H, N, B) || !make_head_map(&tk, k, d, H, M, B) || !make_head_map(&tv, v, d, H, M, B))
+    return SIDLSG_ERR_CUDA;
+  const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
+  if (!g_attn_attr_done) {
+    cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    g_attn_attr_done = true;
+  }
+  dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
+  if (p.dpad <= 128) attn_fwd_kernel<256><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  return check_launch("attention_fwd");
+}

@@ -13,6 +13,7 @@ from torch.autograd import Function
 from ._lib import lib, ptr, dt, stream, require_cuda, F32
 
 _ATTN_SCORE_BYTES = 1 << 30  # materialised score chunk of the fp32-exact attention path
+FLASH_ATTENTION = True         # bf16 mode: tcgen05 flash attention forward (attention_tc.cu)
 
 
 def _grad_of(p):
@@ -250,6 +251,13 @@ class AttentionFn(Function):
         scale = float(d) ** -0.5
         o = torch.empty_like(q)
         cbs = _attn_chunk(B, heads, N, M)
+        if q.dtype == torch.bfloat16 and d % 8 == 0 and 16 <= d <= 192 and FLASH_ATTENTION:
+            # tensor-core flash attention (attention_tc.cu); scores never reach HBM
+            lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+            lib.call("attention_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, N, M, heads, d, stream())
+            ctx.save_for_backward(q, k, v)
+            ctx.cfg = (B, N, M, C, heads, d, scale, cbs)
+            return o
         for b0 in range(0, B, cbs):
             cb = min(cbs, B - b0)
             P = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
@@ -355,9 +363,31 @@ class ConcatFn(Function):
         return da, db
 
 
+class Upsample2xFn(Function):
+    """nearest-neighbour 2x on [B,H,W,C] (materialised so the following 3x3 conv runs on the tensor-core path)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, C = x.shape
+        y = torch.empty((B, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+        lib.call("upsample2x_fwd", ptr(x), ptr(y), B, H, W, C, dt(x), stream())
+        ctx.geom = (B, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C = ctx.geom
+        dy = _c(dy)
+        dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dy.device)
+        lib.call("upsample2x_bwd", ptr(dy), ptr(dx), B, H, W, C, dt(dy), stream())
+        return dx
+
+
 geglu = GegluFn.apply
 silu = SiluFn.apply
 concat = ConcatFn.apply
+upsample2x = Upsample2xFn.apply
 
 
 class NchwToTokensFn(Function):

@@ -208,7 +208,11 @@ class Upsample2D(nn.Module):
 
     def forward(self, x, hw):
         B, HW, C = x.shape
-        y = ops.conv3x3(x.view(B, hw[0], hw[1], C), self.conv.weight, self.conv.bias, up=2)
+        if x.dtype == torch.bfloat16:
+            # tensor-core mode: materialise the 2x copy (HBM-cheap) so the conv is a plain TMA implicit GEMM
+            y = ops.conv3x3(ops.upsample2x(x.view(B, hw[0], hw[1], C)), self.conv.weight, self.conv.bias)
+        else:
+            y = ops.conv3x3(x.view(B, hw[0], hw[1], C), self.conv.weight, self.conv.bias, up=2)
         return y.view(B, -1, C), (y.shape[1], y.shape[2])
 
 

@@ -110,3 +110,33 @@ def test_tc_wgrad_accumulates():
         xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
         ops().conv3x3(xd, wp).backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
     check(wp.grad, wr.grad, 2e-3, "dw accumulated")
+
+
+@pytest.mark.parametrize("B,N,M,C,heads", [(2, 4096, 4096, 320, 8), (2, 1024, 1024, 640, 8), (3, 256, 256, 1280, 8),
+                                           (2, 64, 64, 1280, 8), (2, 4096, 77, 320, 8), (1, 1024, 1024, 640, 10),
+                                           (2, 256, 77, 1280, 20), (1, 200, 333, 128, 2)])
+def test_tc_flash_attention_forward(B, N, M, C, heads):
+    """tcgen05 flash attention vs fp32 softmax(QK^T/sqrt(d))V on bf16-rounded inputs (bf16 P and bf16 output:
+    tolerance 2e-2 of the output scale); backward runs through the fp32-exact recompute path."""
+    g = torch.Generator().manual_seed(4)
+    q = bf(torch.randn(B, N, C, generator=g))
+    k = bf(torch.randn(B, M, C, generator=g))
+    v = bf(torch.randn(B, M, C, generator=g))
+    d = C // heads
+
+    def split(t):
+        return t.view(t.shape[0], t.shape[1], heads, d).transpose(1, 2)
+
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    s = split(qr) @ split(kr).transpose(-1, -2) * d ** -0.5
+    o_ref = (torch.softmax(s, -1) @ split(vr)).transpose(1, 2).reshape(B, N, C)
+    qd, kd, vd = (t.to(DEV).bfloat16().requires_grad_(True) for t in (q, k, v))
+    o = ops().attention(qd, kd, vd, heads)
+    check(o, o_ref, 2e-2, "o")
+    if N * M <= 1024 * 1024:
+        do = bf(torch.randn(B, N, C, generator=g))
+        o_ref.backward(do)
+        o.backward(do.to(DEV).bfloat16())
+        check(qd.grad, qr.grad, 3e-2, "dq")
+        check(kd.grad, kr.grad, 3e-2, "dk")
+        check(vd.grad, vr.grad, 3e-2, "dv")
