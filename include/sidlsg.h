@@ -36,6 +36,8 @@ int sidlsg_version();
 int sidlsg_device_arch(int device);
 /* diagnostics: out (HOST memory) long[2] = {tcgen05 GEMM/conv launches, CUDA-core GEMM/conv launches} */
 int sidlsg_counters(long* out);
+/* 1 if the calling thread's last sidlsg_gemm / sidlsg_conv3x3 / sidlsg_conv3x3_wgrad ran on tcgen05, else 0 */
+int sidlsg_last_path();
 
 /* ---- dense contractions --------------------------------------------------------------------------------
  * C[z][m][n] = alpha * sum_k A[z][m][k] B[z][k][n] (+ bias[n]) (+ rowvec[m / rows_per_vec][n]) (+ res[z][m][n])
@@ -100,6 +102,13 @@ int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int 
  * ref: the attention call of every BasicTransformerBlock.attn1/attn2 (xformers / SDPA in the reference). */
 int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
                          int M, int H, int d, void* stream);
+
+/* Backward of the above with the scores recomputed on the tensor cores: dq [B,N,H*d], dk/dv [B,M,H*d] bf16.
+ * delta: fp32 [B,H,N] scratch (= sum_c o*dout, computed here); dq_acc: fp32 [B,N,H*d] scratch (zeroed here; dQ
+ * partials of the K/V tiles are reduced into it with red.global.add).  d % 8 == 0, 16 <= d <= 80. */
+int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                         const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
+                         int B, int N, int M, int H, int d, void* stream);
 
 /* ---- elementwise ----------------------------------------------------------------------------------------- */
 /* UNet boundary: fp32 NCHW [B,C,HW] <-> token-major [B,HW,C] in the compute dtype (sample in, .sample out). */

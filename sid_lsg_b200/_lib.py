@@ -46,6 +46,7 @@ class _Lib:
         self._dll = None
         self._fns = {}
         self.launches = 0  # number of C-ABI calls that launched kernels (bench.py reports it)
+        self.timer = None  # KernelTimer while bench.py measures per-kernel rooflines
 
     def load(self):
         if self._dll is not None:
@@ -68,10 +69,71 @@ class _Lib:
 
     def call(self, name, *args):
         self.load()
-        st = self._fns["sidlsg_" + name](*args)
+        timer = self.timer
+        if timer is not None and name in timer.work:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            st = self._fns["sidlsg_" + name](*args)
+            ev1.record()
+            path = self._fns["sidlsg_last_path"]() if name in ("gemm", "conv3x3", "conv3x3_wgrad") else 1
+            timer.records.append((name, path, timer.work[name](args), ev0, ev1))
+        else:
+            st = self._fns["sidlsg_" + name](*args)
         if st != 0:
             raise RuntimeError("sidlsg_%s failed (%d): %s" % (name, st, self.last_error()))
         self.launches += 1
+
+
+class KernelTimer:
+    """Per-call CUDA-event timing of selected C-ABI entry points with their ALGORITHMIC work
+    (FLOPs for the contractions, bytes for the HBM-bound kernels); used by bench.py's roofline pass."""
+
+    def __init__(self):
+        def gemm(a):      # ..., M, N, K, nb1, nb2 at positions 23..27
+            return ("flop", 2.0 * a[23] * a[24] * a[25] * a[26] * a[27])
+
+        def conv(a):      # B, Hi, Wi, Kc, Ho, Wo, N at 6..12
+            return ("flop", 2.0 * a[6] * a[10] * a[11] * a[12] * 9 * a[9])
+
+        def wgrad(a):     # B, Hi, Wi, Cin, Ho, Wo, Cout at 3..9
+            return ("flop", 2.0 * a[3] * a[7] * a[8] * a[9] * 9 * a[6])
+
+        def attn(a):      # q,k,v,o,lse,B,N,M,H,d
+            return ("flop", 4.0 * a[5] * a[6] * a[7] * a[8] * a[9])
+
+        def attn_bwd(a):  # 5 contractions (S recompute, dP, dV, dK, dQ)
+            return ("flop", 10.0 * a[-6] * a[-5] * a[-4] * a[-3] * a[-2])
+
+        def gn_fwd(a):    # B, HW, C at 9..11; read x twice (stats + apply), write y
+            return ("byte", 3.0 * a[9] * a[10] * a[11] * (4 if a[15] == 0 else 2))
+
+        def gn_bwd(a):    # B, HW, C at 13..15; read dy,x twice, write dx
+            return ("byte", 5.0 * a[13] * a[14] * a[15] * (4 if a[19] == 0 else 2))
+
+        def adam(a):      # p,g,m,v,ema,shadow,n: read p,g,v(,ema) write p,v(,ema,shadow)
+            n = a[6]
+            return ("byte", n * (20.0 + (8 if a[4] else 0) + (2 if a[5] else 0) + (8 if a[2] else 0)))
+
+        def lsg(a):       # B, CHW at 7,8: 3 reads + 3 writes fp32
+            return ("byte", 24.0 * a[7] * a[8])
+
+        self.work = {"gemm": gemm, "conv3x3": conv, "conv3x3_wgrad": wgrad, "attention_fwd": attn,
+                     "attention_bwd": attn_bwd, "groupnorm_fwd": gn_fwd, "groupnorm_bwd": gn_bwd, "adam_step": adam,
+                     "lsg_loss": lsg}
+        self.records = []
+
+    def summary(self):
+        """-> {key: dict(launches, ms, work, unit)}; key = name or name+'[simt]' for CUDA-core GEMM/conv calls."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, path, (unit, work), ev0, ev1 in self.records:
+            key = name if path else name + "[simt]"
+            d = out.setdefault(key, dict(launches=0, ms=0.0, work=0.0, unit=unit))
+            d["launches"] += 1
+            d["ms"] += ev0.elapsed_time(ev1)
+            d["work"] += work
+        return out
 
 
 lib = _Lib()

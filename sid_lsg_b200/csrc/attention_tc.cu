@@ -285,3 +285,327 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   return check_launch("attention_fwd");
 }
+
+// =====================================================================================================================
+// Backward: dQ, dK, dV with the scores recomputed on the tensor cores (FlashAttention-2 schedule).
+// One CTA owns a 128-row K/V tile of one (batch, head) and walks the query tiles.  Everything is computed in the
+// TRANSPOSED orientation so every operand is a plain TMA tile and no transpose is ever materialised:
+//   S^T  = K Q^T            (A = K tile, B = Q tile, both K-major)              -> TMEM
+//   dP^T = V dO^T           (A = V tile, B = dO tile, both K-major)             -> TMEM
+//   P^T  = exp2(S^T c - lse), dS^T = P^T o (dP^T - delta) * scale               (8 compute warps, one kv row per thread,
+//                                                                                 written as bf16 SWIZZLE_128B tiles)
+//   dV  += P^T dO           (A = P^T tile K-major, B = the SAME dO tile read MN-major)
+//   dK  += dS^T Q           (A = dS^T tile K-major, B = the SAME Q tile read MN-major)
+//   dQ_i = dS K             (A = the dS^T tile read MN-major, B = K tile read MN-major) -> fp32 red.add into dq_acc
+// dK/dV accumulate in TMEM over the whole query loop; dQ partials are reduced across K/V tiles with red.global.add.
+// 320 threads: warps 0-7 compute (two warpgroups split the 128 query columns), warp 8 TMA, warp 9 MMA + TMEM alloc.
+namespace sidlsg {
+
+constexpr int AB_THREADS = 320;
+
+struct AttnBwdParams {
+  int B, H, N, M, d;
+  int dchunks, dpad, q_stages;
+  float scale, scale_log2;
+  const float* lse;      // [B,H,N]
+  const float* delta;    // [B,H,N] = sum_c O dO
+  float* dq_acc;         // [B,N,H*d] fp32, zero-initialised by the caller
+  bf16* dk;
+  bf16* dv;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const int QST = p.q_stages;
+  const uint32_t tile_bytes = p.dchunks * AT_CHUNK;
+  const uint32_t k_smem = smem_base;
+  const uint32_t v_smem = k_smem + tile_bytes;
+  const uint32_t q_smem = v_smem + tile_bytes;
+  const uint32_t do_smem = q_smem + QST * tile_bytes;
+  const uint32_t p_smem = do_smem + QST * tile_bytes;     // P^T  [128 kv][128 q] bf16 (2 chunks)
+  const uint32_t ds_smem = p_smem + 2 * AT_CHUNK;         // dS^T [128 kv][128 q] bf16 (2 chunks)
+  const uint32_t stat_smem = ds_smem + 2 * AT_CHUNK;      // float [2 bufs][2 (lse2, delta)][128]
+  const uint32_t bar_base = stat_smem + 2 * 2 * 128 * 4;
+  const uint32_t kv_full = bar_base, s_full = bar_base + 8, dp_full = bar_base + 16, pds_full = bar_base + 24,
+                 dq_full = bar_base + 32;
+  auto qdo_full = [&](int s) { return bar_base + 40 + 8u * s; };
+  auto qdo_empty = [&](int s) { return bar_base + 56 + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 72;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  float* stat = reinterpret_cast<float*>(smem_raw + (stat_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * AT_BKV, h = blockIdx.y, b = blockIdx.z;
+  const int TQ = (p.N + AT_BQ - 1) / AT_BQ;
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) { printf("sidlsg attention bwd: dynamic smem not 1024-aligned\n"); __trap(); }
+    mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t st_tmem = tmem_base, dp_tmem = tmem_base + 128, dv_tmem = tmem_base + 256,
+                 dk_tmem = tmem_base + 256 + p.dpad, dq_tmem = tmem_base + 256 + 2 * p.dpad;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * tile_bytes);
+      for (int c = 0; c < p.dchunks; ++c) {
+        tma_load_4d(&tmK, kv_full, k_smem + c * AT_CHUNK, c * 64, h, kv0, b);
+        tma_load_4d(&tmV, kv_full, v_smem + c * AT_CHUNK, c * 64, h, kv0, b);
+      }
+      for (int i = 0; i < TQ; ++i) {
+        const int st = i % QST;
+        mbar_wait(qdo_empty(st), ((i / QST) & 1) ^ 1);
+        mbar_expect_tx(qdo_full(st), 2 * tile_bytes);
+        for (int c = 0; c < p.dchunks; ++c) {
+          tma_load_4d(&tmQ, qdo_full(st), q_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, i * AT_BQ, b);
+          tma_load_4d(&tmDO, qdo_full(st), do_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, i * AT_BQ, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const int dsteps = p.dpad >> 4;
+      const uint32_t idesc_s = make_idesc(128, 0, 0);
+      const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
+      const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < TQ; ++i) {
+        const int st = i % QST;
+        mbar_wait(qdo_full(st), (i / QST) & 1);
+        tc_fence_after();
+        const uint32_t qb = q_smem + st * tile_bytes, dob = do_smem + st * tile_bytes;
+        for (int s = 0; s < dsteps; ++s) {
+          const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(st_tmem, make_desc(k_smem + off, 1024, 0), make_desc(qb + off, 1024, 0), idesc_s, s > 0);
+        }
+        tc_commit(s_full);
+        for (int s = 0; s < dsteps; ++s) {
+          const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(dp_tmem, make_desc(v_smem + off, 1024, 0), make_desc(dob + off, 1024, 0), idesc_s, s > 0);
+        }
+        tc_commit(dp_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        for (int s = 0; s < 8; ++s) {      // reduction over the 128 query rows of this tile
+          const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(dv_tmem, make_desc(p_smem + aoff, 1024, 0), make_desc(dob + s * 2048, 1024, AT_CHUNK), idesc_kv,
+                      (i > 0 || s > 0) ? 1u : 0u);
+        }
+        for (int s = 0; s < 8; ++s) {
+          const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(dk_tmem, make_desc(ds_smem + aoff, 1024, 0), make_desc(qb + s * 2048, 1024, AT_CHUNK), idesc_kv,
+                      (i > 0 || s > 0) ? 1u : 0u);
+        }
+        for (int s = 0; s < 8; ++s) {      // reduction over the 128 kv rows: dQ_i = dS K
+          tc_mma_bf16(dq_tmem, make_desc(ds_smem + s * 2048, 1024, AT_CHUNK), make_desc(k_smem + s * 2048, 1024, AT_CHUNK),
+                      idesc_dq, s > 0);
+        }
+        tc_commit(qdo_empty(st));
+        tc_commit(dq_full);
+      }
+    }
+  } else {
+    // ===================== compute warps 0-7 =====================
+    const int wg = warp >> 2;                       // which 64 query columns
+    const int row = (warp & 3) * 32 + lane;         // kv row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bool row_ok = kv0 + row < p.M;
+    const float c = p.scale_log2;
+    const int C = p.H * p.d;
+    const int tid = threadIdx.x;                    // 0..255
+    for (int i = 0; i < TQ; ++i) {
+      float* sb = stat + (i & 1) * 256;
+      {
+        const int qi = i * AT_BQ + (tid & 127);
+        const long gi = ((long)b * p.H + h) * p.N + qi;
+        if (tid < 128) sb[tid] = qi < p.N ? p.lse[gi] * 1.4426950408889634f : INFINITY;
+        else sb[tid] = qi < p.N ? p.delta[gi] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      const float* lse2 = sb + wg * 64;
+      const float* dl = sb + 128 + wg * 64;
+      uint32_t pk[32];
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32_nowait(st_tmem + lane_off + wg * 64 + half * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = row_ok ? ex2f(fmaf(__uint_as_float(r[j]), c, -lse2[half * 32 + j])) : 0.f;
+          float p1 = row_ok ? ex2f(fmaf(__uint_as_float(r[j + 1]), c, -lse2[half * 32 + j + 1])) : 0.f;
+          pk[half * 16 + (j >> 1)] = pack_bf16(p0, p1);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          st_shared_v4(p_smem + sw128_offset(row, wg * 64 + half * 32 + 8 * qd, AT_CHUNK), pk[half * 16 + 4 * qd],
+                       pk[half * 16 + 4 * qd + 1], pk[half * 16 + 4 * qd + 2], pk[half * 16 + 4 * qd + 3]);
+      }
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32], dsk[16];
+        tmem_ld32_nowait(dp_tmem + lane_off + wg * 64 + half * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          __nv_bfloat162 pp = *reinterpret_cast<__nv_bfloat162*>(&pk[half * 16 + (j >> 1)]);
+          float d0 = __low2float(pp) * (__uint_as_float(r[j]) - dl[half * 32 + j]) * p.scale;
+          float d1 = __high2float(pp) * (__uint_as_float(r[j + 1]) - dl[half * 32 + j + 1]) * p.scale;
+          dsk[j >> 1] = pack_bf16(d0, d1);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          st_shared_v4(ds_smem + sw128_offset(row, wg * 64 + half * 32 + 8 * qd, AT_CHUNK), dsk[4 * qd], dsk[4 * qd + 1],
+                       dsk[4 * qd + 2], dsk[4 * qd + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // drain dQ_i (TMEM lane = query row) into the fp32 accumulator; 16-column blocks alternate between warpgroups
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      {
+        const int q = i * AT_BQ + row;
+        float* dqrow = p.dq_acc + ((long)b * p.N + q) * C + h * p.d;
+        for (int blk = wg; blk * 16 < p.dpad; blk += 2) {
+          uint32_t r[16];
+          tmem_ld16_nowait(dq_tmem + lane_off + blk * 16, r);
+          tmem_wait_ld();
+          if (q < p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (blk * 16 + j < p.d)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqrow + blk * 16 + j),
+                             "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                             "f"(__uint_as_float(r[j + 3])) : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    // the last dq_full commit covered every MMA: dV / dK accumulators are final. wg0 stores dV, wg1 stores dK.
+    {
+      const uint32_t acc = wg == 0 ? dv_tmem : dk_tmem;
+      bf16* out = (wg == 0 ? p.dv : p.dk) + ((long)b * p.M + kv0 + row) * C + h * p.d;
+      for (int cc = 0; cc < p.dpad; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(acc + lane_off + cc, r);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (cc + 8 * hh < p.d) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(r[8 * hh + 0]), __uint_as_float(r[8 * hh + 1]));
+              o.y = pack_bf16(__uint_as_float(r[8 * hh + 2]), __uint_as_float(r[8 * hh + 3]));
+              o.z = pack_bf16(__uint_as_float(r[8 * hh + 4]), __uint_as_float(r[8 * hh + 5]));
+              o.w = pack_bf16(__uint_as_float(r[8 * hh + 6]), __uint_as_float(r[8 * hh + 7]));
+              *reinterpret_cast<uint4*>(out + cc + 8 * hh) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// delta[b,h,q] = sum_c O[b,q,h*d+c] * dO[b,q,h*d+c]   (one warp per (b,q,h))
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                  int B, int N, int H, int d) {
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long total = (long)B * N * H;
+  if (w >= total) return;
+  const int hh = (int)(w % H);
+  const long bq = w / H;
+  const long base = bq * (long)H * d + (long)hh * d;
+  float s = 0.f;
+  for (int c = lane * 2; c < d; c += 64) {
+    __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + base + c);
+    __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(dout + base + c);
+    s += __low2float(a) * __low2float(g) + __high2float(a) * __high2float(g);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long b = bq / N, q = bq % N;
+    delta[(b * H + hh) * N + q] = s;
+  }
+}
+
+static bool g_attn_bwd_attr_done = false;
+
+}  // namespace sidlsg
+
+extern "C" int sidlsg_cast(const void* x, void* y, long n, int in_dtype, int out_dtype, void* stream);
+
+// dq_acc: fp32 [B,N,H*d] scratch (zeroed here), delta: fp32 [B,H,N] scratch.  dq/dk/dv bf16 outputs.
+// Supports d % 8 == 0, 16 <= d <= 80 (TMEM: 256 + 3*dpad <= 512 columns); returns SIDLSG_ERR_UNSUPPORTED otherwise.
+extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                    const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
+                                    int B, int N, int M, int H, int d, void* stream) {
+  if (!tc_enabled()) { set_error("attention_bwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
+  const int dpad = (d + 15) & ~15;
+  if (d % 8 || d < 16 || 256 + 3 * dpad > 512 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
+    set_error("attention_bwd: unsupported shape B=%d N=%d M=%d H=%d d=%d", B, N, M, H, d);
+    return SIDLSG_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long nq = (long)B * N * H;
+  cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * N * H * d, st);
+  attn_delta_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, N, H, d);
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.N = N; p.M = M; p.d = d;
+  p.dchunks = (d + 63) / 64;
+  p.dpad = dpad;
+  p.q_stages = p.dchunks == 1 ? 2 : 1;
+  p.scale = 1.f / sqrtf((float)d);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+  CUtensorMap tq, tk, tv, tdo;
+  if (!make_head_map(&tq, q, d, H, N, B) || !make_head_map(&tk, k, d, H, M, B) || !make_head_map(&tv, v, d, H, M, B) ||
+      !make_head_map(&tdo, dout, d, H, N, B))
+    return SIDLSG_ERR_CUDA;
+  const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256;
+  if (!g_attn_bwd_attr_done) {
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    g_attn_bwd_attr_done = true;
+  }
+  dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
+  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, p);
+  int r = check_launch("attention_bwd");
+  if (r != SIDLSG_OK) return r;
+  // dq (bf16) = dq_acc (fp32)
+  return sidlsg_cast(dq_acc, dq, (long)B * N * H * d, SIDLSG_F32, SIDLSG_BF16, stream);
+}

@@ -207,12 +207,14 @@ gemm_core(LA la, LB lb, Epilogue<TO> epi, int M, int N, int K, int ksplit, int a
 }
 
 long g_simt_launches = 0;
+extern thread_local int g_last_path;
 
 template <class LA, class LB, class TO>
 static int launch_core(LA la, LB lb, Epilogue<TO> epi, int M, int N, int K, int nbatch, int ksplit,
                        int a_kc, int b_kc, cudaStream_t st) {
   if (M <= 0 || N <= 0 || nbatch <= 0) return SIDLSG_OK;
   __atomic_add_fetch(&g_simt_launches, 1, __ATOMIC_RELAXED);
+  g_last_path = 0;
   bool big = (long)M * N >= 128L * 128 * 64 && M >= 128 && N >= 96;
   if (big) {
     dim3 grid(cdiv(N, 128), cdiv(M, 128), nbatch * ksplit);

@@ -403,12 +403,14 @@ static int pick_block_n(int n, bool mn_major) {
 }
 
 long g_tc_launches = 0;
+thread_local int g_last_path = 0;   // 1 = the last GEMM/conv entry point of this thread ran on tcgen05
 extern long g_simt_launches;
 
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
   long tiles = (long)p.m_tiles * p.n_tiles * p.splits;
   if (tiles <= 0) return SIDLSG_OK;
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
+  g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
   return check_launch("gemm_tc");
@@ -593,6 +595,7 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
 }  // namespace sidlsg
 
 // diagnostics: out[0] = tcgen05 GEMM/conv launches, out[1] = CUDA-core GEMM/conv launches (host memory)
+extern "C" int sidlsg_last_path() { return sidlsg::g_last_path; }
 extern "C" int sidlsg_counters(long* out) {
   out[0] = sidlsg::g_tc_launches;
   out[1] = sidlsg::g_simt_launches;

@@ -14,6 +14,7 @@ from ._lib import lib, ptr, dt, stream, require_cuda, F32
 
 _ATTN_SCORE_BYTES = 1 << 30  # materialised score chunk of the fp32-exact attention path
 FLASH_ATTENTION = True         # bf16 mode: tcgen05 flash attention forward (attention_tc.cu)
+FLASH_ATTENTION_BWD = True     # ... and backward (d <= 80; d = 160 layers use the recompute path)
 
 
 def _grad_of(p):
@@ -255,9 +256,14 @@ class AttentionFn(Function):
             # tensor-core flash attention (attention_tc.cu); scores never reach HBM
             lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
             lib.call("attention_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, N, M, heads, d, stream())
-            ctx.save_for_backward(q, k, v)
+            ctx.flash_bwd = d <= 80 and FLASH_ATTENTION_BWD
+            if ctx.flash_bwd:
+                ctx.save_for_backward(q, k, v, o, lse)
+            else:
+                ctx.save_for_backward(q, k, v)
             ctx.cfg = (B, N, M, C, heads, d, scale, cbs)
             return o
+        ctx.flash_bwd = False
         for b0 in range(0, B, cbs):
             cb = min(cbs, B - b0)
             P = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
@@ -270,9 +276,17 @@ class AttentionFn(Function):
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v = ctx.saved_tensors
         B, N, M, C, heads, d, scale, cbs = ctx.cfg
         do = _c(do)
+        if ctx.flash_bwd:
+            q, k, v, o, lse = ctx.saved_tensors
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            delta = torch.empty_like(lse)
+            dq_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+            lib.call("attention_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dq_acc),
+                     ptr(dq), ptr(dk), ptr(dv), B, N, M, heads, d, stream())
+            return dq, dk, dv, None
+        q, k, v = ctx.saved_tensors
         dq = torch.empty_like(q)
         dk = torch.empty_like(k)
         dv = torch.empty_like(v)

@@ -115,9 +115,9 @@ def test_tc_wgrad_accumulates():
 @pytest.mark.parametrize("B,N,M,C,heads", [(2, 4096, 4096, 320, 8), (2, 1024, 1024, 640, 8), (3, 256, 256, 1280, 8),
                                            (2, 64, 64, 1280, 8), (2, 4096, 77, 320, 8), (1, 1024, 1024, 640, 10),
                                            (2, 256, 77, 1280, 20), (1, 200, 333, 128, 2)])
-def test_tc_flash_attention_forward(B, N, M, C, heads):
+def test_tc_flash_attention(B, N, M, C, heads):
     """tcgen05 flash attention vs fp32 softmax(QK^T/sqrt(d))V on bf16-rounded inputs (bf16 P and bf16 output:
-    tolerance 2e-2 of the output scale); backward runs through the fp32-exact recompute path."""
+    tolerance 2e-2 of the output scale); backward = tcgen05 flash backward for d <= 80, recompute path for d = 160."""
     g = torch.Generator().manual_seed(4)
     q = bf(torch.randn(B, N, C, generator=g))
     k = bf(torch.randn(B, M, C, generator=g))
@@ -133,7 +133,7 @@ def test_tc_flash_attention_forward(B, N, M, C, heads):
     qd, kd, vd = (t.to(DEV).bfloat16().requires_grad_(True) for t in (q, k, v))
     o = ops().attention(qd, kd, vd, heads)
     check(o, o_ref, 2e-2, "o")
-    if N * M <= 1024 * 1024:
+    if N * M <= 1024 * 1024 or d <= 80:
         do = bf(torch.randn(B, N, C, generator=g))
         o_ref.backward(do)
         o.backward(do.to(DEV).bfloat16())
