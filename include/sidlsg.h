@@ -127,6 +127,8 @@ int sidlsg_concat2(const void* a, const void* b, void* out, long M, int Ca, int 
 int sidlsg_split2(const void* in, void* a, void* b, long M, int Ca, int Cb, int dtype, void* stream);
 int sidlsg_upsample2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int sidlsg_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+/* y[b,2i,2j,:] = x[b,i,j,:], zeros elsewhere: turns the stride-2 conv data gradient into a stride-1 one */
+int sidlsg_zero_insert2x(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 /* out[g][n] (+)= sum_r x[g][r][n]: bias gradients (G=1) and time_emb_proj gradients (G=B, R=HW) */
 int sidlsg_colsum(const void* x, float* out, int G, long R, int N, int accumulate, int dtype, void* stream);
 int sidlsg_cast(const void* x, void* y, long n, int in_dtype, int out_dtype, void* stream);

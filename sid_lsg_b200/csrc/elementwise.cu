@@ -201,6 +201,24 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ 
   store_vec<T, V>(dx + ((b * H + iy) * W + ix) * C + c, acc);
 }
 
+// zero insertion: y[b, 2i, 2j, :] = x[b, i, j, :], zeros elsewhere (data gradient of a stride-2 conv becomes a stride-1 one)
+template <class T, int V>
+__global__ void zero_insert2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int vpr = C / V;
+  long total = (long)B * 4 * H * W * vpr;
+  if (i >= total) return;
+  int c = (int)(i % vpr) * V;
+  long r = i / vpr;
+  int ox = (int)(r % (2 * W));
+  r /= 2 * W;
+  int oy = (int)(r % (2 * H));
+  long b = r / (2 * H);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (!(ox & 1) && !(oy & 1)) v = *reinterpret_cast<const uint4*>(x + ((b * H + oy / 2) * W + ox / 2) * C + c);
+  *reinterpret_cast<uint4*>(y + ((b * 2 * H + oy) * 2 * W + ox) * C + c) = v;
+}
+
 // ---- out[g][n] (+)= sum_r x[g][r][n]   (fp32 out; bias and timestep-projection gradients) --------------
 template <class T>
 __global__ void __launch_bounds__(256)
@@ -365,6 +383,12 @@ extern "C" int sidlsg_upsample2x_fwd(const void* x, void* y, int B, int H, int W
   if (B == 0) return SIDLSG_OK;
   SID_DISPATCH_DTYPE(dtype, T, (upsample2x_fwd_kernel<T, VecOf<T>::n><<<EW_GRID((long)B * 4 * H * W * (C / VecOf<T>::n))>>>((const T*)x, (T*)y, B, H, W, C)));
   return check_launch("upsample2x_fwd");
+}
+extern "C" int sidlsg_zero_insert2x(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
+  REQUIRE_VEC("zero_insert2x", C, dtype);
+  if (B == 0) return SIDLSG_OK;
+  SID_DISPATCH_DTYPE(dtype, T, (zero_insert2x_kernel<T, VecOf<T>::n><<<EW_GRID((long)B * 4 * H * W * (C / VecOf<T>::n))>>>((const T*)x, (T*)y, B, H, W, C)));
+  return check_launch("zero_insert2x");
 }
 extern "C" int sidlsg_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
   REQUIRE_VEC("upsample2x_bwd", C, dtype);

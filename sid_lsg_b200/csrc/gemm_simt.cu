@@ -237,6 +237,112 @@ static int pick_ksplit(int M, int N, int K, int nbatch) {
   return (int)s;
 }
 
+// ---- skinny fp32 GEMMs (timestep-embedding path: M = batch <= 32 rows, or a reduction over <= 32 rows) ----------
+// weight-bandwidth bound: the weight matrix is streamed exactly once with coalesced / 128-bit accesses.
+constexpr int SK_M = 32;
+
+// C[m][n] = sum_k A[m][k] W[n][k]   (W K-contiguous): one warp per output column n, lanes split K
+__global__ void __launch_bounds__(256)
+skinny_nt_kernel(const float* __restrict__ A, long a_sm, const float* __restrict__ W, long w_sn, float* __restrict__ C,
+                 long ldc, const float* __restrict__ bias, const float* __restrict__ res, long ldr, int M, int N, int K,
+                 float alpha, int accumulate) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[SK_M];
+#pragma unroll
+  for (int m = 0; m < SK_M; ++m) acc[m] = 0.f;
+  const float* w = W + (long)n * w_sn;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 wv = (k + 3 < K) ? *reinterpret_cast<const float4*>(w + k)
+                            : make_float4(w[k], k + 1 < K ? w[k + 1] : 0.f, k + 2 < K ? w[k + 2] : 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < SK_M; ++m) {
+      if (m < M) {
+        const float* a = A + (long)m * a_sm + k;
+        float4 av = (k + 3 < K) ? *reinterpret_cast<const float4*>(a)
+                                : make_float4(a[0], k + 1 < K ? a[1] : 0.f, k + 2 < K ? a[2] : 0.f, 0.f);
+        acc[m] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[m]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SK_M; ++m) {
+    if (m < M) {
+      float v = warp_sum(acc[m]);
+      if (lane == 0) {
+        v *= alpha;
+        if (bias) v += bias[n];
+        if (res) v += res[(long)m * ldr + n];
+        float* dst = C + (long)m * ldc + n;
+        *dst = accumulate ? *dst + v : v;
+      }
+    }
+  }
+}
+
+// C[m][n] = sum_k A[m][k] B[k][n]   (B n-contiguous): one thread per column n, every k row read coalesced
+__global__ void __launch_bounds__(128)
+skinny_nn_kernel(const float* __restrict__ A, long a_sm, long a_sk, const float* __restrict__ Bm, long b_sk,
+                 float* __restrict__ C, long ldc, int M, int N, int K, float alpha, int accumulate) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  float acc[SK_M];
+#pragma unroll
+  for (int m = 0; m < SK_M; ++m) acc[m] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float bv = Bm[(long)k * b_sk + n];
+#pragma unroll
+    for (int m = 0; m < SK_M; ++m)
+      if (m < M) acc[m] = fmaf(A[(long)m * a_sm + (long)k * a_sk], bv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < SK_M; ++m)
+    if (m < M) {
+      float* dst = C + (long)m * ldc + n;
+      *dst = accumulate ? *dst + alpha * acc[m] : alpha * acc[m];
+    }
+}
+
+// C[m][n] (+)= sum_{k < K <= 32} A[k][m] B[k][n]   (both read along their contiguous dimension): weight gradients
+__global__ void __launch_bounds__(256)
+skinny_tn_kernel(const float* __restrict__ A, long a_sk, const float* __restrict__ Bm, long b_sk, float* __restrict__ C,
+                 long ldc, int M, int N, int K, float alpha, int accumulate) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(A[(long)k * a_sk + m], Bm[(long)k * b_sk + n], acc);
+  float* dst = C + (long)m * ldc + n;
+  *dst = accumulate ? *dst + alpha * acc : alpha * acc;
+}
+
+// returns 1 if handled
+static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long b_sn, long b_sk, float* c, long ldc,
+                      const float* bias, const float* res, long ldr, const float* rowvec, float alpha, int accumulate,
+                      int M, int N, int K, cudaStream_t st) {
+  if (rowvec) return 0;
+  if (M <= 4 * SK_M && a_sk == 1 && b_sk == 1 && (a_sm % 4) == 0 && (b_sn % 4) == 0 &&
+      ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    for (int m0 = 0; m0 < M; m0 += SK_M)
+      skinny_nt_kernel<<<cdiv(N, 8), 256, 0, st>>>(a + m0 * a_sm, a_sm, b, b_sn, c + m0 * ldc, ldc, bias,
+                                                    res ? res + m0 * ldr : nullptr, ldr, min(SK_M, M - m0), N, K, alpha,
+                                                    accumulate);
+    return check_launch("skinny_nt") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
+  }
+  if (M <= 4 * SK_M && b_sn == 1 && !bias && !res) {
+    for (int m0 = 0; m0 < M; m0 += SK_M)
+      skinny_nn_kernel<<<cdiv(N, 128), 128, 0, st>>>(a + m0 * a_sm, a_sm, a_sk, b, b_sk, c + m0 * ldc, ldc,
+                                                      min(SK_M, M - m0), N, K, alpha, accumulate);
+    return check_launch("skinny_nn") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
+  }
+  if (K <= 4 * SK_M && a_sm == 1 && b_sn == 1 && !bias && !res && M <= 65535) {
+    skinny_tn_kernel<<<dim3(cdiv(N, 256), M), 256, 0, st>>>(a, a_sk, b, b_sk, c, ldc, M, N, K, alpha, accumulate);
+    return check_launch("skinny_tn") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
+  }
+  return 0;
+}
+
 // tensor-core (tcgen05) paths of gemm_tc.cu: return 1 = handled, 0 = shape not eligible, <0 = error
 int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, long b_sk, void* c, long ldc,
                 const float* bias, const void* res, long ldr, const float* rowvec, int rows_per_vec, float alpha,
@@ -264,6 +370,11 @@ extern "C" int sidlsg_gemm(const void* a, long a_sm, long a_sk, long a_sb1, long
   if (nbatch == 1 && M > 0 && N > 0 && K > 0) {
     int r = tc_gemm_try(a, a_sm, a_sk, b, b_sn, b_sk, c, ldc, bias, res, ldr, rowvec, rows_per_vec, alpha, accumulate,
                         M, N, K, in_dtype, out_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
+  }
+  if (nbatch == 1 && in_dtype == SIDLSG_F32 && out_dtype == SIDLSG_F32 && M > 0 && N > 0 && K > 0) {
+    int r = skinny_try((const float*)a, a_sm, a_sk, (const float*)b, b_sn, b_sk, (float*)c, ldc, bias, (const float*)res,
+                       ldr, rowvec, alpha, accumulate, M, N, K, st);
     if (r != 0) return r < 0 ? r : SIDLSG_OK;
   }
   int ksplit = 1;

@@ -44,6 +44,7 @@ struct TcParams {
   int H, W;                 // image extent of the tensor the boxes are cut from
   int cchunks;              // 64-channel chunks per tap in the reduction (conv fwd / dgrad)
   int flip;                 // dgrad: sample at -tap offset
+  int cstride;              // convolution stride (1 or 2): TMA traversal stride over W and H
   int n_tiles_per_tap;      // conv wgrad: N tiles per tap
   int cin;                  // conv wgrad: channels per tap (column offset = tap*cin + n_in)
   // epilogue
@@ -162,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             int oy = tap / 3 - 1, ox = tap % 3 - 1;
             if (p.flip) { oy = -oy; ox = -ox; }
-            tma_load_4d(&tmA, fb, sa, c0, ox, ah0 + oy, ab0);
+            tma_load_4d(&tmA, fb, sa, c0, ox, ah0 * p.cstride + oy, ab0);
           }
           // ---- B ----
           if (p.b_mode == B_K2D) {
@@ -176,7 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int bb0 = pix0 / hw;
             const int bh0 = (pix0 - bb0 * hw) / p.W;
             const int oy = t.tap / 3 - 1, ox = t.tap % 3 - 1;
-            for (int j = 0; j < b_boxes; ++j) tma_load_4d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, ox, bh0 + oy, bb0);
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_4d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, ox, bh0 * p.cstride + oy, bb0);
           }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -339,12 +341,13 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, SWIZZLE_128B, inner box 64 elements.  dims/strides innermost first; strides[i] (bytes) for dim i+1.
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box) {
+              const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  // with a traversal stride s, TMA loads ceil(box/s) elements: box counts are given in LOADED elements here
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; es[i] = elem_strides ? elem_strides[i] : 1; bx[i] = box[i] * es[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = CUDA_SUCCESS;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -446,7 +449,7 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, l
 
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N;
+  p.M = M; p.N = N; p.cstride = 1;
   p.block_n = pick_block_n(N, b_mn);
   p.m_tiles = (M + TC_BM - 1) / TC_BM;
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
@@ -500,15 +503,17 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
                    int B, int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride,
                    int up, int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st) {
   if (!tc_enabled() || in_dtype != SIDLSG_BF16 || out_dtype != SIDLSG_BF16) return 0;
-  if (stride != 1 || up != 1 || transposed || accumulate) return 0;
-  if (Hi != Ho || Wi != Wo || (Kc % 64) || (N % 8) || !aligned16(x) || !aligned16(w)) return 0;
+  if ((stride != 1 && stride != 2) || up != 1 || transposed || accumulate) return 0;
+  if ((Kc % 64) || (N % 8) || !aligned16(x) || !aligned16(w)) return 0;
   const bool fwd = !flip && w_sk == 1 && w_stap == Kc && w_sn == 9L * Kc;
   const bool dgrad = flip && w_sn == 1 && w_stap == N && w_sk == 9L * N;
   if (!fwd && !dgrad) return 0;
-  if (dgrad && (N % 64)) return 0;
+  if (dgrad && ((N % 64) || stride != 1)) return 0;
+  if (stride == 1 && (Hi != Ho || Wi != Wo)) return 0;
+  if (stride == 2 && (Hi != 2 * Ho || Wi != 2 * Wo)) return 0;
   uint32_t wt, ht, nt;
-  if (!conv_box(Hi, Wi, 128, &wt, &ht, &nt)) return 0;
-  const long M = (long)B * Hi * Wi;
+  if (!conv_box(Ho, Wo, 128, &wt, &ht, &nt)) return 0;
+  const long M = (long)B * Ho * Wo;
   if (M < 128) return 0;
 
   TcParams p;
@@ -522,7 +527,7 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   p.kb_total = 9 * p.cchunks;
   p.a_mode = A_CONV;
   p.b_mode = fwd ? B_K2D : B_W3D;
-  p.H = Hi; p.W = Wi; p.flip = flip;
+  p.H = Ho; p.W = Wo; p.flip = flip; p.cstride = stride;
   p.c = y; p.ldc = N; p.out_f32 = 0;
   p.bias = bias; p.res = res; p.ldr = N; p.rowvec = rowvec; p.rows_per_vec = Ho * Wo; p.alpha = 1.f;
 
@@ -531,7 +536,8 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
     uint64_t d[4] = {(uint64_t)Kc, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t s[3] = {(uint64_t)Kc * 2, (uint64_t)Wi * Kc * 2, (uint64_t)Hi * Wi * Kc * 2};
     uint32_t bx[4] = {64, wt, ht, nt};
-    if (!make_map(&ta, x, 4, d, s, bx)) return SIDLSG_ERR_CUDA;
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (!make_map(&ta, x, 4, d, s, bx, es)) return SIDLSG_ERR_CUDA;
   }
   if (fwd) {
     uint64_t d[2] = {(uint64_t)9 * Kc, (uint64_t)N}, s[1] = {(uint64_t)9 * Kc * 2};
@@ -552,12 +558,14 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
                          int Cout, long dw_sco, long dw_stap, long dw_sci, int stride, int up, int accumulate,
                          int in_dtype, cudaStream_t st) {
   if (!tc_enabled() || in_dtype != SIDLSG_BF16) return 0;
-  if (stride != 1 || up != 1 || Hi != Ho || Wi != Wo) return 0;
+  if ((stride != 1 && stride != 2) || up != 1) return 0;
+  if (stride == 1 && (Hi != Ho || Wi != Wo)) return 0;
+  if (stride == 2 && (Hi != 2 * Ho || Wi != 2 * Wo)) return 0;
   if ((Cin % 64) || (Cout % 8) || Cout < 64 || !aligned16(x) || !aligned16(dy) || !aligned16(dw)) return 0;
   if (!(dw_sci == 1 && dw_stap == Cin && dw_sco == 9L * Cin)) return 0;
   uint32_t wt, ht, nt;
-  if (!conv_box(Hi, Wi, 64, &wt, &ht, &nt)) return 0;
-  const long npix = (long)B * Hi * Wi;
+  if (!conv_box(Ho, Wo, 64, &wt, &ht, &nt)) return 0;
+  const long npix = (long)B * Ho * Wo;
   if (npix < 64 || (npix % 64)) return 0;
   if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * 9 * Cin, st);
 
@@ -573,7 +581,7 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
   p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
   p.a_mode = A_MN2D;
   p.b_mode = B_CONV;
-  p.H = Hi; p.W = Wi;
+  p.H = Ho; p.W = Wo; p.cstride = stride;
   p.c = dw; p.ldc = 9L * Cin; p.out_f32 = 1; p.alpha = 1.f; p.atomic = 1; p.rows_per_vec = 1;
 
   CUtensorMap ta, tb;
@@ -586,7 +594,8 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
     uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Wi * Cin * 2, (uint64_t)Hi * Wi * Cin * 2};
     uint32_t bx[4] = {64, wt, ht, nt};
-    if (!make_map(&tb, x, 4, d, s, bx)) return SIDLSG_ERR_CUDA;
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (!make_map(&tb, x, 4, d, s, bx, es)) return SIDLSG_ERR_CUDA;
   }
   int r = launch_tc(ta, tb, p, st);
   return r == SIDLSG_OK ? 1 : r;

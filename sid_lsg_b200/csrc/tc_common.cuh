@@ -138,8 +138,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, uint32_t chun
 }
 
 // host: bf16 tensor map, SWIZZLE_128B; dims/box innermost first; strides_bytes[i] is the stride of dim i+1
+// box[] counts LOADED elements per dim; elem_strides (optional) = TMA traversal stride per dim
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box);
+              const uint32_t* box, const uint32_t* elem_strides = nullptr);
 bool tc_enabled();
 int tc_num_sms();
 

@@ -123,8 +123,15 @@ class Conv3x3Fn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dfull = torch.empty((B, H * up, W * up, C), dtype=dy.dtype, device=dy.device)
-            lib.call("conv3x3", ptr(dy), ptr(wc), ptr(dfull), None, None, None, B, Ho, Wo, N, H * up, W * up, C,
-                     1, C, 9 * C, stride, 1, 1 if stride > 1 else 0, 1, 0, dt(dy), dt(dfull), stream())
+            if stride == 2 and dy.dtype == torch.bfloat16 and H == 2 * Ho and W == 2 * Wo:
+                # tensor-core mode: zero-insert dy so the transposed conv is a plain stride-1 data gradient
+                dyz = torch.empty((B, H, W, N), dtype=dy.dtype, device=dy.device)
+                lib.call("zero_insert2x", ptr(dy), ptr(dyz), B, Ho, Wo, N, dt(dy), stream())
+                lib.call("conv3x3", ptr(dyz), ptr(wc), ptr(dfull), None, None, None, B, H, W, N, H, W, C,
+                         1, C, 9 * C, 1, 1, 0, 1, 0, dt(dy), dt(dfull), stream())
+            else:
+                lib.call("conv3x3", ptr(dy), ptr(wc), ptr(dfull), None, None, None, B, Ho, Wo, N, H * up, W * up, C,
+                         1, C, 9 * C, stride, 1, 1 if stride > 1 else 0, 1, 0, dt(dy), dt(dfull), stream())
             if up == 2:
                 dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dy.device)
                 lib.call("upsample2x_bwd", ptr(dfull), ptr(dx), B, H, W, C, dt(dy), stream())

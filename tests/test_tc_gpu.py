@@ -70,17 +70,19 @@ def test_tc_linear(M, K, N):
     check(bp.grad, br.grad, 2e-3, "db")
 
 
-@pytest.mark.parametrize("B,H,C,N", [(2, 16, 64, 64), (1, 64, 64, 128), (3, 32, 128, 64), (4, 8, 320, 320),
-                                     (2, 16, 192, 320), (1, 64, 320, 320), (5, 8, 64, 192)])
-def test_tc_conv3x3(B, H, C, N):
+@pytest.mark.parametrize("B,H,C,N,stride", [(2, 16, 64, 64, 1), (1, 64, 64, 128, 1), (3, 32, 128, 64, 1),
+                                            (4, 8, 320, 320, 1), (2, 16, 192, 320, 1), (1, 64, 320, 320, 1),
+                                            (5, 8, 64, 192, 1), (2, 32, 64, 128, 2), (4, 16, 128, 128, 2),
+                                            (1, 64, 320, 320, 2), (3, 16, 64, 64, 2)])
+def test_tc_conv3x3(B, H, C, N, stride):
     g = torch.Generator().manual_seed(1)
     x = bf(torch.randn(B, C, H, H, generator=g))
     w = bf(torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C))
     b = torch.randn(N, generator=g)
     rv = torch.randn(B, N, generator=g)
-    res = bf(torch.randn(B, N, H, H, generator=g))
+    res = bf(torch.randn(B, N, H // stride, H // stride, generator=g))
     xr, wr, br, rvr = (t.clone().requires_grad_(True) for t in (x, w, b, rv))
-    yr = F.conv2d(xr, wr, br, padding=1) + rvr[:, :, None, None] + res
+    yr = F.conv2d(xr, wr, br, padding=1, stride=stride) + rvr[:, :, None, None] + res
     dy = bf(torch.randn(yr.shape, generator=g))
     yr.backward(dy)
     xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16().requires_grad_(True)
@@ -89,7 +91,7 @@ def test_tc_conv3x3(B, H, C, N):
     bp = torch.nn.Parameter(b.to(DEV))
     bp.grad = torch.zeros_like(bp)
     resd = res.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16()
-    y = ops().conv3x3(xd, wp, bp, resd, rvd)
+    y = ops().conv3x3(xd, wp, bp, resd, rvd, stride)
     y.backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
     check(y.permute(0, 3, 1, 2), yr, 1.5e-2, "y")
     check(xd.grad.permute(0, 3, 1, 2), xr.grad, 1.5e-2, "dx")
