@@ -71,15 +71,16 @@ int sidlsg_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int Hi
 
 /* ---- normalisation -----------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) on [B,HW,C]; writes mean/rstd [B,G] and the per-(b,c) affine a/sh [B,C] that the
- * backward (and a fused consumer) reuse.  ws: double[2*B*C] scratch.
+ * backward (and a fused consumer) reuse.  ws: sidlsg_groupnorm_ws_bytes(B,HW,C,dtype) bytes of scratch.
  * ref: ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm (eps 1e-6), conv_norm_out + conv_act. */
+long sidlsg_groupnorm_ws_bytes(int B, int HW, int C, int dtype);
 int sidlsg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                         float* rstd, float* a, float* sh, double* ws, int B, int HW, int C, int G,
+                         float* rstd, float* a, float* sh, void* ws, int B, int HW, int C, int G,
                          float eps, int silu, int in_dtype, int out_dtype, void* stream);
 /* P, Q: float[B*C] scratch; dgamma/dbeta fp32 (may be null), accumulate: 0 overwrite, 1 += */
 int sidlsg_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                          const float* rstd, const float* a, const float* sh, void* dx, float* dgamma,
-                         float* dbeta, double* ws, float* P, float* Q, int B, int HW, int C, int G,
+                         float* dbeta, void* ws, float* P, float* Q, int B, int HW, int C, int G,
                          int silu, int accumulate, int dtype, void* stream);
 /* ref: BasicTransformerBlock.norm1/norm2/norm3 (LayerNorm, eps 1e-5, affine). dgamma/dbeta are accumulated. */
 int sidlsg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,

@@ -27,7 +27,7 @@ def parse_header(path=HEADER):
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(const char\*|int)\s+(sidlsg_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const char\*|int|long)\s+(sidlsg_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         argtypes = []
         for a in [x.strip() for x in args.split(",") if x.strip()]:
@@ -37,7 +37,8 @@ def parse_header(path=HEADER):
                 t = re.sub(r"\b(const|unsigned)\b", "", a).strip()
                 t = " ".join(t.split()[:-1])  # drop the parameter name
                 argtypes.append(_CT[t])
-        out[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+        rt = ctypes.c_char_p if ret.startswith("const char") else (ctypes.c_long if ret == "long" else ctypes.c_int)
+        out[name] = (rt, argtypes)
     return out
 
 
@@ -62,6 +63,11 @@ class _Lib:
             fn.argtypes = argtypes
             self._fns[name] = fn
         return self
+
+    def query(self, name, *args):
+        """value-returning entry points (no status code, no launch)."""
+        self.load()
+        return self._fns["sidlsg_" + name](*args)
 
     def last_error(self):
         self.load()

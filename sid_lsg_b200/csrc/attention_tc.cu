@@ -39,6 +39,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 issue once for two lanes of data)
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -145,59 +169,144 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ===================== softmax / output (warps 0-3) =====================
+    // Instruction budget per score: FFMA2 (1/2) + MUFU.EX2 (1) + FADD2 (1/2) + FMNMX3 (1/2) + F2FP (1/2) = 3 issue
+    // slots, so the loop is bound by the 16/clk/SM MUFU pipe.  Full tiles after the first run ONE pass over S with
+    // the running max (speculative); the tile is redone only if its max exceeds the running max by more than 2^8.
     const int row = warp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float c = p.scale_log2;
+    const uint64_t c2 = pack2(c, c);
+    const uint32_t p_row = p_smem + row * 128;
+    const int rx = row & 7;
     float m_used = -INFINITY, l_run = 0.f;
+
+    auto tile_max = [&](int n_valid) {
+      float mx = -INFINITY;
+      if (n_valid == AT_BKV) {
+#pragma unroll
+        for (int cc = 0; cc < AT_BKV; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
+        }
+      } else {
+        for (int cc = 0; cc < n_valid; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (cc + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      return mx;
+    };
+    // P = exp2(s*c - m*c) -> bf16 smem tile; returns the row sum, tracks the raw row max in mx
+    auto tile_exp = [&](int n_valid, float m, float& mx) {
+      const float nmc = -m * c;
+      const uint64_t nmc2 = pack2(nmc, nmc);
+      uint64_t ls2 = pack2(0.f, 0.f);
+      float ls = 0.f;
+      if (n_valid == AT_BKV) {
+#pragma unroll
+        for (int cc = 0; cc < AT_BKV; cc += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            mx = fmaxf(fmaxf(mx, x0), x1);
+            float t0, t1;
+            unpack2(ffma2(pack2(x0, x1), c2, nmc2), t0, t1);
+            const float p0 = ex2f(t0), p1 = ex2f(t1);
+            ls2 = fadd2(ls2, pack2(p0, p1));
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int u = ((cc & 63) >> 3) + qd;
+            st_shared_v4(p_row + (cc >> 6) * AT_CHUNK + ((u ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                         pk[4 * qd + 3]);
+          }
+        }
+        float a0, a1;
+        unpack2(ls2, a0, a1);
+        ls = a0 + a1;
+      } else {
+        for (int cc = 0; cc < n_valid; cc += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const bool v0 = cc + i < n_valid, v1 = cc + i + 1 < n_valid;
+            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            if (v0) mx = fmaxf(mx, x0);
+            if (v1) mx = fmaxf(mx, x1);
+            const float p0 = v0 ? ex2f(fmaf(x0, c, nmc)) : 0.f;
+            const float p1 = v1 ? ex2f(fmaf(x1, c, nmc)) : 0.f;
+            ls += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            st_shared_v4(p_smem + sw128_offset(row, cc + 8 * qd, AT_CHUNK), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                         pk[4 * qd + 3]);
+        }
+      }
+      return ls;
+    };
+    // O *= f (per-lane factor) in TMEM; all 32 lanes call it together
+    auto rescale_o = [&](float f) {
+      for (int cc = 0; cc < p.dpad; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(o_tmem + lane_off + cc, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+        tmem_st16(o_tmem + lane_off + cc, r);
+      }
+      tmem_wait_st();
+    };
+
     for (int j = 0; j < T; ++j) {
       const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+      const bool spec = j > 0 && n_valid == AT_BKV;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-      for (int cc = 0; cc < n_valid; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32_nowait(s_tmem + lane_off + cc, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (cc + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      const float m_new = fmaxf(m_used, mx);
-      const bool need = (m_new - m_used) * c > 8.f;
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);   // P V of the previous tile retired: O and the P tile are ours again
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
-          for (int cc = 0; cc < p.dpad; cc += 16) {
-            uint32_t r[16];
-            tmem_ld16_nowait(o_tmem + lane_off + cc, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st16(o_tmem + lane_off + cc, r);
+      if (!spec) {
+        const float m_new = fmaxf(m_used, tile_max(n_valid));
+        const bool need = (m_new - m_used) * c > 8.f;
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);   // P V of the previous tile retired: O and the P tile are ours again
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+            rescale_o(f);
+            l_run *= f;
           }
-          tmem_wait_st();
+        }
+        if (need) m_used = m_new;
+      } else {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      float mx = -INFINITY;
+      float l_tile = tile_exp(n_valid, m_used, mx);
+      if (spec) {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) * c > 8.f;
+        if (__any_sync(0xffffffffu, need)) {       // rare: this tile raised the max by more than 2^8 -> redo it
+          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+          rescale_o(f);
           l_run *= f;
+          if (need) m_used = m_new;
+          l_tile = tile_exp(n_valid, m_used, mx);
         }
       }
-      if (need) m_used = m_new;
-      const float mc = m_used * c;
-      for (int cc = 0; cc < n_valid; cc += 32) {
-        uint32_t r[32], pk[16];
-        tmem_ld32_nowait(s_tmem + lane_off + cc, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (cc + i < n_valid) ? ex2f(fmaf(__uint_as_float(r[i]), c, -mc)) : 0.f;
-          float p1 = (cc + i + 1 < n_valid) ? ex2f(fmaf(__uint_as_float(r[i + 1]), c, -mc)) : 0.f;
-          l_run += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
-        }
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
-          st_shared_v4(p_smem + sw128_offset(row, cc + 8 * qd, AT_CHUNK), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
-                       pk[4 * qd + 3]);
-      }
+      l_run += l_tile;
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -309,7 +418,8 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const float* lse;      // [B,H,N]
   const float* delta;    // [B,H,N] = sum_c O dO
-  float* dq_acc;         // [B,N,H*d] fp32, zero-initialised by the caller
+  float* dq_acc;         // [B,N,H*d] fp32, zero-initialised by the caller (written through tmDQ)
+  int stage_alias;       // dQ staging aliases the P^T/dS^T tiles (d > 64)
   bf16* dk;
   bf16* dv;
 };
@@ -319,7 +429,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const int QST = p.q_stages;
@@ -331,7 +441,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t p_smem = do_smem + QST * tile_bytes;     // P^T  [128 kv][128 q] bf16 (2 chunks)
   const uint32_t ds_smem = p_smem + 2 * AT_CHUNK;         // dS^T [128 kv][128 q] bf16 (2 chunks)
   const uint32_t stat_smem = ds_smem + 2 * AT_CHUNK;      // float [2 bufs][2 (lse2, delta)][128]
-  const uint32_t bar_base = stat_smem + 2 * 2 * 128 * 4;
+  // dQ staging for the TMA reduce-add: fp32 [chunks of 32 columns][128 rows][128 B] SWIZZLE_128B.  Own region when
+  // it fits (d <= 64), otherwise it aliases the P^T/dS^T tiles (dead once the tile's MMAs have retired).
+  const int dq_chunks = (p.d + 31) >> 5;
+  const uint32_t dq_stage = p.stage_alias ? p_smem : stat_smem + 2 * 2 * 128 * 4;
+  const uint32_t bar_base = stat_smem + 2 * 2 * 128 * 4 + (p.stage_alias ? 0 : dq_chunks * AT_CHUNK);
   const uint32_t kv_full = bar_base, s_full = bar_base + 8, dp_full = bar_base + 16, pds_full = bar_base + 24,
                  dq_full = bar_base + 32;
   auto qdo_full = [&](int s) { return bar_base + 40 + 8u * s; };
@@ -352,6 +466,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -431,35 +546,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c = p.scale_log2;
     const int C = p.H * p.d;
     const int tid = threadIdx.x;                    // 0..255
+    const uint64_t c2 = pack2(c, c), scale2 = pack2(p.scale, p.scale);
+    const uint32_t p_row = p_smem + row * 128, ds_row = ds_smem + row * 128;
+    const int rx = row & 7;
     for (int i = 0; i < TQ; ++i) {
       float* sb = stat + (i & 1) * 256;
       {
         const int qi = i * AT_BQ + (tid & 127);
         const long gi = ((long)b * p.H + h) * p.N + qi;
-        if (tid < 128) sb[tid] = qi < p.N ? p.lse[gi] * 1.4426950408889634f : INFINITY;
-        else sb[tid] = qi < p.N ? p.delta[gi] : 0.f;
+        if (tid < 128) sb[tid] = qi < p.N ? -p.lse[gi] * 1.4426950408889634f : -INFINITY;
+        else sb[tid] = qi < p.N ? -p.delta[gi] : 0.f;
       }
       named_bar_sync(1, 256);
-      const float* lse2 = sb + wg * 64;
-      const float* dl = sb + 128 + wg * 64;
-      uint32_t pk[32];
+      // sb holds the NEGATED statistics so they feed the packed FFMA2 / FADD2 directly
+      const float* nlse2 = sb + wg * 64;
+      const float* ndl = sb + 128 + wg * 64;
+      uint64_t ps2[32];                      // P * scale for this thread's 64 query columns (fp32 pairs)
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
+        uint32_t r[32], pk[16];
         tmem_ld32_nowait(st_tmem + lane_off + wg * 64 + half * 32, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = row_ok ? ex2f(fmaf(__uint_as_float(r[j]), c, -lse2[half * 32 + j])) : 0.f;
-          float p1 = row_ok ? ex2f(fmaf(__uint_as_float(r[j + 1]), c, -lse2[half * 32 + j + 1])) : 0.f;
-          pk[half * 16 + (j >> 1)] = pack_bf16(p0, p1);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 nl = *reinterpret_cast<const float4*>(nlse2 + half * 32 + j);
+          float t0, t1, t2, t3;
+          unpack2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(nl.x, nl.y)), t0, t1);
+          unpack2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), t2, t3);
+          float p0 = ex2f(t0), p1 = ex2f(t1), p2 = ex2f(t2), p3 = ex2f(t3);
+          if (!row_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+          pk[j >> 1] = pack_bf16(p0, p1);
+          pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+          ps2[half * 16 + (j >> 1)] = fmul2(pack2(p0, p1), scale2);
+          ps2[half * 16 + (j >> 1) + 1] = fmul2(pack2(p2, p3), scale2);
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
-          st_shared_v4(p_smem + sw128_offset(row, wg * 64 + half * 32 + 8 * qd, AT_CHUNK), pk[half * 16 + 4 * qd],
-                       pk[half * 16 + 4 * qd + 1], pk[half * 16 + 4 * qd + 2], pk[half * 16 + 4 * qd + 3]);
+          st_shared_v4(p_row + wg * AT_CHUNK + (((half * 4 + qd) ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                       pk[4 * qd + 3]);
       }
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
@@ -469,44 +595,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32_nowait(dp_tmem + lane_off + wg * 64 + half * 32, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          __nv_bfloat162 pp = *reinterpret_cast<__nv_bfloat162*>(&pk[half * 16 + (j >> 1)]);
-          float d0 = __low2float(pp) * (__uint_as_float(r[j]) - dl[half * 32 + j]) * p.scale;
-          float d1 = __high2float(pp) * (__uint_as_float(r[j + 1]) - dl[half * 32 + j + 1]) * p.scale;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 nd = *reinterpret_cast<const float4*>(ndl + half * 32 + j);
+          float d0, d1, d2, d3;
+          unpack2(fmul2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(nd.x, nd.y)),
+                        ps2[half * 16 + (j >> 1)]), d0, d1);
+          unpack2(fmul2(fadd2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pack2(nd.z, nd.w)),
+                        ps2[half * 16 + (j >> 1) + 1]), d2, d3);
           dsk[j >> 1] = pack_bf16(d0, d1);
+          dsk[(j >> 1) + 1] = pack_bf16(d2, d3);
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
-          st_shared_v4(ds_smem + sw128_offset(row, wg * 64 + half * 32 + 8 * qd, AT_CHUNK), dsk[4 * qd], dsk[4 * qd + 1],
+          st_shared_v4(ds_row + wg * AT_CHUNK + (((half * 4 + qd) ^ rx) << 4), dsk[4 * qd], dsk[4 * qd + 1],
                        dsk[4 * qd + 2], dsk[4 * qd + 3]);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // drain dQ_i (TMEM lane = query row) into the fp32 accumulator; 16-column blocks alternate between warpgroups
+      // drain dQ_i (TMEM lane = query row): stage the fp32 tile in smem, then ONE thread hands it to the TMA unit
+      // as a bulk reduce-add into dq_acc (the partials of the K/V tiles meet in L2, no per-thread atomics)
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      {
-        const int q = i * AT_BQ + row;
-        float* dqrow = p.dq_acc + ((long)b * p.N + q) * C + h * p.d;
-        for (int blk = wg; blk * 16 < p.dpad; blk += 2) {
-          uint32_t r[16];
-          tmem_ld16_nowait(dq_tmem + lane_off + blk * 16, r);
-          tmem_wait_ld();
-          if (q < p.N) {
+      if (tid == 0) tma_wait_group_read0();        // the previous reduce has finished reading the staging tile
+      named_bar_sync(2, 256);
+      for (int blk = wg; blk * 16 < p.dpad; blk += 2) {
+        uint32_t r[16];
+        tmem_ld16_nowait(dq_tmem + lane_off + blk * 16, r);
+        tmem_wait_ld();
+        const uint32_t base = dq_stage + (blk >> 1) * AT_CHUNK + row * 128;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (blk * 16 + j < p.d)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqrow + blk * 16 + j),
-                             "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                             "f"(__uint_as_float(r[j + 3])) : "memory");
-            }
-          }
-        }
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(base + ((((blk & 1) * 4 + j) ^ rx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       }
       tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (tid == 0) {
+        for (int ch = 0; ch < dq_chunks; ++ch) tma_reduce_add_4d(&tmDQ, dq_stage + ch * AT_CHUNK, ch * 32, h, i * AT_BQ, b);
+        tma_commit_group();
+        if (p.stage_alias) tma_wait_group_read0();
+      }
+      if (p.stage_alias) named_bar_sync(2, 256);   // P^T / dS^T tiles may be rewritten only after the TMA read them
     }
+    if (tid == 0) tma_wait_group_read0();
     // the last dq_full commit covered every MMA: dV / dK accumulators are final. wg0 stores dV, wg1 stores dK.
     {
       const uint32_t acc = wg == 0 ? dv_tmem : dk_tmem;
@@ -593,17 +726,26 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   p.scale = 1.f / sqrtf((float)d);
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
-  CUtensorMap tq, tk, tv, tdo;
+  p.stage_alias = d > 64;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   if (!make_head_map(&tq, q, d, H, N, B) || !make_head_map(&tk, k, d, H, M, B) || !make_head_map(&tv, v, d, H, M, B) ||
       !make_head_map(&tdo, dout, d, H, N, B))
     return SIDLSG_ERR_CUDA;
-  const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256;
+  {
+    const long C = (long)H * d;
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)d * 4, (uint64_t)C * 4, (uint64_t)N * C * 4};
+    uint32_t box[4] = {32, 1, 128, 1};
+    if (!make_map(&tdq, dq_acc, 4, dims, strides, box, nullptr, 1)) return SIDLSG_ERR_CUDA;
+  }
+  const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256 +
+                   (p.stage_alias ? 0 : ((d + 31) / 32) * AT_CHUNK);
   if (!g_attn_bwd_attr_done) {
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_bwd_attr_done = true;
   }
   dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
-  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;
   // dq (bf16) = dq_acc (fp32)

@@ -341,7 +341,7 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, SWIZZLE_128B, inner box 64 elements.  dims/strides innermost first; strides[i] (bytes) for dim i+1.
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, const uint32_t* elem_strides) {
+              const uint32_t* box, const uint32_t* elem_strides, int f32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t gd[5], gs[4];
@@ -351,7 +351,7 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = CUDA_SUCCESS;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+    r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_ERROR_INVALID_CONTEXT && r != CUDA_ERROR_NOT_INITIALIZED) break;

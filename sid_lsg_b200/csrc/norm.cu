@@ -7,65 +7,118 @@
 namespace sidlsg {
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_MAXSLOT = 10;  // C <= 2560
+constexpr int GN_MAXC = 2560;
+constexpr int GN_MAXCHUNKS = 64;
 
-// ---- GroupNorm statistics: sums[b][c][2] partial per-channel sums (double) -------------------------
-template <class T>
+template <class T> struct GnVec;   // elements per 16-byte access
+template <> struct GnVec<float> { static constexpr int n = 4; };
+template <> struct GnVec<bf16> { static constexpr int n = 8; };
+
+template <class T, int V>
+__device__ __forceinline__ void gn_load(const T* p, float* out) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V; ++i) out[i] = to_f(e[i]);
+}
+template <class T, int V>
+__device__ __forceinline__ void gn_store(T* p, const float* in) {
+  uint4 raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V; ++i) e[i] = from_f<T>(in[i]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+// Launch geometry shared by the statistics kernels: blockDim = (VX, RY); a thread owns V consecutive channels of
+// channel slab `it` (C is covered by `iters` slabs of VX*V channels) and walks rows r0+y, r0+y+RY, ...
+struct GnGeom { int vx, ry, iters, chunks, rows_per_chunk; };
+
+static GnGeom gn_geom(int B, int HW, int C, int V) {
+  GnGeom g;
+  int vpr = C / V;
+  g.iters = (vpr + GN_THREADS - 1) / GN_THREADS;
+  g.vx = (vpr + g.iters - 1) / g.iters;
+  g.ry = GN_THREADS / g.vx;
+  if (g.ry < 1) g.ry = 1;
+  if (g.ry > HW) g.ry = HW;
+  int want = (4 * 148 + B - 1) / B;                 // ~4 waves of CTAs
+  int maxc = HW / (g.ry * 2);                       // at least 2 rows per thread
+  if (maxc < 1) maxc = 1;
+  g.chunks = want < maxc ? want : maxc;
+  if (g.chunks > GN_MAXCHUNKS) g.chunks = GN_MAXCHUNKS;
+  if (g.chunks < 1) g.chunks = 1;
+  g.rows_per_chunk = (HW + g.chunks - 1) / g.chunks;
+  g.chunks = (HW + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  return g;
+}
+
+// ---- forward statistics: partial[b][chunk][c] = (sum x, sum x^2) over the chunk's rows, fp32 ---------------------
+template <class T, int V>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_partial_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW, int C, int rows_per_block) {
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(HW, r0 + rows_per_block);
-  float s[GN_MAXSLOT], q[GN_MAXSLOT];
-#pragma unroll
-  for (int i = 0; i < GN_MAXSLOT; ++i) s[i] = q[i] = 0.f;
+gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partial, int HW, int C, int vpr, int iters,
+                int rows_per_chunk) {
+  extern __shared__ float red[];   // [2][RY][VX*V]
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int tx = threadIdx.x, ty = threadIdx.y, VX = blockDim.x, RY = blockDim.y;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   const T* xb = x + (long)b * HW * C;
-  for (int r = r0; r < r1; ++r) {
-    const T* row = xb + (long)r * C;
+  for (int it = 0; it < iters; ++it) {
+    const int v = it * VX + tx;
+    float s[V], q[V];
 #pragma unroll
-    for (int i = 0; i < GN_MAXSLOT; ++i) {
-      int c = threadIdx.x + i * GN_THREADS;
-      if (c < C) {
-        float v = to_f(row[c]);
-        s[i] += v;
-        q[i] = fmaf(v, v, q[i]);
+    for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+    if (v < vpr) {
+      for (int r = r0 + ty; r < r1; r += RY) {
+        float e[V];
+        gn_load<T, V>(xb + (long)r * C + v * V, e);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s[i] += e[i]; q[i] = fmaf(e[i], e[i], q[i]); }
       }
     }
-  }
+    const int W = VX * V;
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < GN_MAXSLOT; ++i) {
-    int c = threadIdx.x + i * GN_THREADS;
-    if (c < C) {
-      atomicAdd(&sums[((long)b * C + c) * 2 + 0], (double)s[i]);
-      atomicAdd(&sums[((long)b * C + c) * 2 + 1], (double)q[i]);
+    for (int i = 0; i < V; ++i) { red[ty * W + tx * V + i] = s[i]; red[(RY + ty) * W + tx * V + i] = q[i]; }
+    __syncthreads();
+    for (int c = ty * VX + tx; c < W; c += VX * RY) {
+      float ss = 0.f, qq = 0.f;
+      for (int y = 0; y < RY; ++y) { ss += red[y * W + c]; qq += red[(RY + y) * W + c]; }
+      const int ch = it * W + c;
+      if (ch < C) partial[((long)b * chunks + chunk) * C + ch] = make_float2(ss, qq);
     }
   }
 }
 
-// one thread per (b, c): group statistics -> per-channel affine  y = x*a + sh
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ mean_out,
-                                   float* __restrict__ rstd_out, float* __restrict__ a, float* __restrict__ sh,
-                                   int B, int C, int G, int HW, float eps) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * C) return;
-  int b = idx / C, c = idx - b * C;
-  int cpg = C / G, g = c / cpg;
+// one warp per (b, group): combine chunks x channels in double -> mean / rstd, then the per-channel affine
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ a,
+                   float* __restrict__ sh, int B, int C, int G, int HW, int chunks, float eps) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * G) return;
+  const int b = w / G, g = w - b * G, cpg = C / G;
   double s = 0, q = 0;
-  for (int j = 0; j < cpg; ++j) {
-    s += sums[((long)b * C + g * cpg + j) * 2 + 0];
-    q += sums[((long)b * C + g * cpg + j) * 2 + 1];
+  for (int i = lane; i < chunks * cpg; i += 32) {
+    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
+    const float2 v = partial[((long)b * chunks + ch) * C + c];
+    s += v.x; q += v.y;
   }
-  double n = (double)HW * cpg;
-  double mean = s / n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  const double n = (double)HW * cpg;
+  const double mean = s / n;
   double var = q / n - mean * mean;
   if (var < 0) var = 0;
-  float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  float mf = (float)mean;
-  if (c == g * cpg) { mean_out[b * G + g] = mf; rstd_out[b * G + g] = rstd; }
-  float ga = gamma[c];
-  a[idx] = rstd * ga;
-  sh[idx] = beta[c] - mf * rstd * ga;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mf = (float)mean;
+  if (lane == 0) { mean_out[w] = mf; rstd_out[w] = rstd; }
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float ga = gamma[c];
+    a[(long)b * C + c] = rstd * ga;
+    sh[(long)b * C + c] = beta[c] - mf * rstd * ga;
+  }
 }
 
 template <class TI, class TO, int VEC>
@@ -99,82 +152,94 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
   }
 }
 
-// ---- GroupNorm backward ------------------------------------------------------------------------------
-// partial per-(b,c) sums of dz and dz*xhat ; dz = dy * silu'(pre) (pre = x*a+sh) or dy
-template <class T>
+// ---- backward ---------------------------------------------------------------------------------------------------
+// partial[b][chunk][c] = (sum dz, sum dz*xhat); dz = dy * silu'(x*a+sh) (or dy)
+template <class T, int V>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_partial_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ a,
-                      const float* __restrict__ sh, const float* __restrict__ mean, const float* __restrict__ rstd,
-                      double* __restrict__ sums, int HW, int C, int G, int rows_per_block, int silu) {
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(HW, r0 + rows_per_block);
+gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ a,
+                    const float* __restrict__ sh, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    float2* __restrict__ partial, int HW, int C, int G, int vpr, int iters, int rows_per_chunk, int silu) {
+  extern __shared__ float red[];
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int tx = threadIdx.x, ty = threadIdx.y, VX = blockDim.x, RY = blockDim.y;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   const int cpg = C / G;
-  float s[GN_MAXSLOT], q[GN_MAXSLOT], av[GN_MAXSLOT], sv[GN_MAXSLOT], mu[GN_MAXSLOT], rs[GN_MAXSLOT];
-#pragma unroll
-  for (int i = 0; i < GN_MAXSLOT; ++i) {
-    s[i] = q[i] = 0.f;
-    int c = threadIdx.x + i * GN_THREADS;
-    if (c < C) {
-      av[i] = a[(long)b * C + c]; sv[i] = sh[(long)b * C + c];
-      mu[i] = mean[b * G + c / cpg]; rs[i] = rstd[b * G + c / cpg];
-    } else { av[i] = sv[i] = mu[i] = rs[i] = 0.f; }
-  }
   const long base = (long)b * HW * C;
-  for (int r = r0; r < r1; ++r) {
-    const long ro = base + (long)r * C;
+  for (int it = 0; it < iters; ++it) {
+    const int v = it * VX + tx;
+    float s[V], q[V], av[V], sv[V], mu[V], rs[V];
 #pragma unroll
-    for (int i = 0; i < GN_MAXSLOT; ++i) {
-      int c = threadIdx.x + i * GN_THREADS;
-      if (c < C) {
-        float xv = to_f(x[ro + c]);
-        float dz = to_f(dy[ro + c]);
-        if (silu) dz *= silu_grad_f(fmaf(xv, av[i], sv[i]));
-        s[i] += dz;
-        q[i] = fmaf(dz, (xv - mu[i]) * rs[i], q[i]);
+    for (int i = 0; i < V; ++i) {
+      s[i] = q[i] = 0.f;
+      const int c = v * V + i;
+      if (v < vpr) {
+        av[i] = a[(long)b * C + c]; sv[i] = sh[(long)b * C + c];
+        mu[i] = mean[b * G + c / cpg]; rs[i] = rstd[b * G + c / cpg];
+      } else { av[i] = sv[i] = mu[i] = rs[i] = 0.f; }
+    }
+    if (v < vpr) {
+      for (int r = r0 + ty; r < r1; r += RY) {
+        float xe[V], de[V];
+        gn_load<T, V>(x + base + (long)r * C + v * V, xe);
+        gn_load<T, V>(dy + base + (long)r * C + v * V, de);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float dz = de[i];
+          if (silu) dz *= silu_grad_f(fmaf(xe[i], av[i], sv[i]));
+          s[i] += dz;
+          q[i] = fmaf(dz, (xe[i] - mu[i]) * rs[i], q[i]);
+        }
       }
     }
-  }
+    const int W = VX * V;
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < GN_MAXSLOT; ++i) {
-    int c = threadIdx.x + i * GN_THREADS;
-    if (c < C) {
-      atomicAdd(&sums[((long)b * C + c) * 2 + 0], (double)s[i]);
-      atomicAdd(&sums[((long)b * C + c) * 2 + 1], (double)q[i]);
+    for (int i = 0; i < V; ++i) { red[ty * W + tx * V + i] = s[i]; red[(RY + ty) * W + tx * V + i] = q[i]; }
+    __syncthreads();
+    for (int c = ty * VX + tx; c < W; c += VX * RY) {
+      float ss = 0.f, qq = 0.f;
+      for (int y = 0; y < RY; ++y) { ss += red[y * W + c]; qq += red[(RY + y) * W + c]; }
+      const int ch = it * W + c;
+      if (ch < C) partial[((long)b * chunks + chunk) * C + ch] = make_float2(ss, qq);
     }
   }
 }
 
-// per (b,c): coefficients of dx = A*dz + x*P + Q
-__global__ void gn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                       float* __restrict__ P, float* __restrict__ Q, int B, int C, int G, int HW) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * C) return;
-  int b = idx / C, c = idx - b * C;
-  int cpg = C / G, g = c / cpg;
+// one warp per (b, group): coefficients of dx = A*dz + x*P + Q
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ P,
+                       float* __restrict__ Q, int B, int C, int G, int HW, int chunks) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * G) return;
+  const int b = w / G, g = w - b * G, cpg = C / G;
   double S1 = 0, S2 = 0;
-  for (int j = 0; j < cpg; ++j) {
-    int cc = g * cpg + j;
-    double ga = gamma[cc];
-    S1 += ga * sums[((long)b * C + cc) * 2 + 0];
-    S2 += ga * sums[((long)b * C + cc) * 2 + 1];
+  for (int i = lane; i < chunks * cpg; i += 32) {
+    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
+    const float2 v = partial[((long)b * chunks + ch) * C + c];
+    const double ga = gamma[c];
+    S1 += ga * v.x; S2 += ga * v.y;
   }
-  double n = (double)HW * cpg;
-  double m = mean[b * G + g], r = rstd[b * G + g];
-  P[idx] = (float)(-r * r * S2 / n);
-  Q[idx] = (float)(-r * S1 / n + m * r * r * S2 / n);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { S1 += __shfl_xor_sync(0xffffffffu, S1, o); S2 += __shfl_xor_sync(0xffffffffu, S2, o); }
+  const double n = (double)HW * cpg;
+  const double m = mean[w], r = rstd[w];
+  const float Pv = (float)(-r * r * S2 / n), Qv = (float)(-r * S1 / n + m * r * r * S2 / n);
+  for (int j = lane; j < cpg; j += 32) {
+    P[(long)b * C + g * cpg + j] = Pv;
+    Q[(long)b * C + g * cpg + j] = Qv;
+  }
 }
 
-// dgamma[c] (+)= sum_b sums[b,c,1] ; dbeta[c] (+)= sum_b sums[b,c,0]
-__global__ void gn_bwd_param_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int B, int C, int accumulate) {
+// dgamma[c] (+)= sum_{b,chunk} partial.y ; dbeta[c] (+)= sum partial.x
+__global__ void gn_bwd_param_kernel(const float2* __restrict__ partial, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int B, int C, int chunks, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0, q = 0;
-  for (int b = 0; b < B; ++b) {
-    s += sums[((long)b * C + c) * 2 + 0];
-    q += sums[((long)b * C + c) * 2 + 1];
+  for (int i = 0; i < B * chunks; ++i) {
+    const float2 v = partial[(long)i * C + c];
+    s += v.x; q += v.y;
   }
   if (accumulate) { dgamma[c] += (float)q; dbeta[c] += (float)s; }
   else { dgamma[c] = (float)q; dbeta[c] = (float)s; }
@@ -305,24 +370,33 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
 
 using namespace sidlsg;
 
-static int gn_rows_per_block(int HW, int B) {
-  int rpb = 64;
-  while (rpb > 8 && (long)cdiv(HW, rpb) * B < 592) rpb >>= 1;
-  return rpb;
+// scratch bytes the GroupNorm entry points need for `ws` (per-chunk fp32 partial sums)
+extern "C" long sidlsg_groupnorm_ws_bytes(int B, int HW, int C, int dtype) {
+  if (B <= 0 || HW <= 0 || C <= 0) return 16;
+  GnGeom g = gn_geom(B, HW, C, dtype == SIDLSG_F32 ? 4 : 8);
+  return (long)sizeof(float2) * B * g.chunks * C;
 }
 
-// workspace: double[B*C*2] sums (zeroed here).  Outputs mean/rstd [B,G] and per-(b,c) affine a/sh [B,C].
+template <class T>
+static void gn_launch_stats(const T* x, float2* ws, int B, int HW, int C, cudaStream_t st) {
+  constexpr int V = GnVec<T>::n;
+  GnGeom g = gn_geom(B, HW, C, V);
+  size_t sm = sizeof(float) * 2 * g.ry * g.vx * V;
+  gn_stats_kernel<T, V><<<dim3(g.chunks, B), dim3(g.vx, g.ry), sm, st>>>(x, ws, HW, C, C / V, g.iters, g.rows_per_chunk);
+}
+
+// ws: sidlsg_groupnorm_ws_bytes(B,HW,C,in_dtype) bytes.  Outputs mean/rstd [B,G] and the per-(b,c) affine a/sh [B,C].
 extern "C" int sidlsg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                                    float* rstd, float* a, float* sh, double* ws, int B, int HW, int C, int G,
+                                    float* rstd, float* a, float* sh, void* ws, int B, int HW, int C, int G,
                                     float eps, int silu, int in_dtype, int out_dtype, void* stream) {
-  if (C > GN_THREADS * GN_MAXSLOT || C % G || C % 8) { set_error("groupnorm: unsupported C=%d G=%d", C, G); return SIDLSG_ERR_ARG; }
+  if (C > GN_MAXC || C % G || C % 8) { set_error("groupnorm: unsupported C=%d G=%d", C, G); return SIDLSG_ERR_ARG; }
+  if (B == 0 || HW == 0) return SIDLSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)B * C, st);
-  int rpb = gn_rows_per_block(HW, B);
-  dim3 grid(cdiv(HW, rpb), B);
-  if (in_dtype == SIDLSG_F32) gn_partial_kernel<float><<<grid, GN_THREADS, 0, st>>>((const float*)x, ws, HW, C, rpb);
-  else gn_partial_kernel<bf16><<<grid, GN_THREADS, 0, st>>>((const bf16*)x, ws, HW, C, rpb);
-  gn_finalize_kernel<<<cdiv((long)B * C, 256), 256, 0, st>>>(ws, gamma, beta, mean, rstd, a, sh, B, C, G, HW, eps);
+  float2* part = (float2*)ws;
+  GnGeom g = gn_geom(B, HW, C, in_dtype == SIDLSG_F32 ? 4 : 8);
+  if (in_dtype == SIDLSG_F32) gn_launch_stats<float>((const float*)x, part, B, HW, C, st);
+  else gn_launch_stats<bf16>((const bf16*)x, part, B, HW, C, st);
+  gn_finalize_kernel<<<cdiv((long)B * G * 32, 256), 256, 0, st>>>(part, gamma, beta, mean, rstd, a, sh, B, C, G, HW, g.chunks, eps);
   long total = (long)B * HW * C;
   if (in_dtype == SIDLSG_F32 && out_dtype == SIDLSG_F32)
     gn_apply_kernel<float, float, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)x, a, sh, (float*)y, total / 4, HW * C, C, silu);
@@ -334,24 +408,26 @@ extern "C" int sidlsg_groupnorm_fwd(const void* x, const float* gamma, const flo
   return check_launch("groupnorm_fwd");
 }
 
-// ws: double[B*C*2]; P,Q: float[B*C] scratch.  dgamma/dbeta fp32 (accumulate flag), may be null.
+// ws as above; P,Q: float[B*C] scratch.  dgamma/dbeta fp32 (accumulate flag), may be null.
 extern "C" int sidlsg_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                                     const float* rstd, const float* a, const float* sh, void* dx, float* dgamma,
-                                    float* dbeta, double* ws, float* P, float* Q, int B, int HW, int C, int G,
+                                    float* dbeta, void* ws, float* P, float* Q, int B, int HW, int C, int G,
                                     int silu, int accumulate, int dtype, void* stream) {
-  if (C > GN_THREADS * GN_MAXSLOT || C % G || C % 8) { set_error("groupnorm_bwd: unsupported C=%d G=%d", C, G); return SIDLSG_ERR_ARG; }
+  if (C > GN_MAXC || C % G || C % 8) { set_error("groupnorm_bwd: unsupported C=%d G=%d", C, G); return SIDLSG_ERR_ARG; }
+  if (B == 0 || HW == 0) return SIDLSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)B * C, st);
-  int rpb = gn_rows_per_block(HW, B);
-  dim3 grid(cdiv(HW, rpb), B);
+  float2* part = (float2*)ws;
   long total = (long)B * HW * C;
-  if (dtype == SIDLSG_F32) {
-    gn_bwd_partial_kernel<float><<<grid, GN_THREADS, 0, st>>>((const float*)dy, (const float*)x, a, sh, mean, rstd, ws, HW, C, G, rpb, silu);
-  } else {
-    gn_bwd_partial_kernel<bf16><<<grid, GN_THREADS, 0, st>>>((const bf16*)dy, (const bf16*)x, a, sh, mean, rstd, ws, HW, C, G, rpb, silu);
-  }
-  gn_bwd_finalize_kernel<<<cdiv((long)B * C, 256), 256, 0, st>>>(ws, gamma, mean, rstd, P, Q, B, C, G, HW);
-  if (dgamma && dbeta) gn_bwd_param_kernel<<<cdiv(C, 256), 256, 0, st>>>(ws, dgamma, dbeta, B, C, accumulate);
+  const int V = dtype == SIDLSG_F32 ? 4 : 8;
+  GnGeom g = gn_geom(B, HW, C, V);
+  size_t sm = sizeof(float) * 2 * g.ry * g.vx * V;
+  dim3 grid(g.chunks, B), block(g.vx, g.ry);
+  if (dtype == SIDLSG_F32)
+    gn_bwd_stats_kernel<float, 4><<<grid, block, sm, st>>>((const float*)dy, (const float*)x, a, sh, mean, rstd, part, HW, C, G, C / 4, g.iters, g.rows_per_chunk, silu);
+  else
+    gn_bwd_stats_kernel<bf16, 8><<<grid, block, sm, st>>>((const bf16*)dy, (const bf16*)x, a, sh, mean, rstd, part, HW, C, G, C / 8, g.iters, g.rows_per_chunk, silu);
+  gn_bwd_finalize_kernel<<<cdiv((long)B * G * 32, 256), 256, 0, st>>>(part, gamma, mean, rstd, P, Q, B, C, G, HW, g.chunks);
+  if (dgamma && dbeta) gn_bwd_param_kernel<<<cdiv(C, 128), 128, 0, st>>>(part, dgamma, dbeta, B, C, g.chunks, accumulate);
   if (dtype == SIDLSG_F32)
     gn_bwd_apply_kernel<float, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)dy, (const float*)x, a, sh, P, Q, (float*)dx, total / 4, HW * C, C, silu);
   else

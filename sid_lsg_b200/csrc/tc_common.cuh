@@ -52,6 +52,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// smem tile -> global with an fp32 add performed by the TMA unit / L2 (bulk reduction; out-of-bounds elements are clipped)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -139,8 +146,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, uint32_t chun
 
 // host: bf16 tensor map, SWIZZLE_128B; dims/box innermost first; strides_bytes[i] is the stride of dim i+1
 // box[] counts LOADED elements per dim; elem_strides (optional) = TMA traversal stride per dim
+// f32 = 1 builds an fp32 map (inner box <= 32 elements for the 128-byte swizzle)
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, const uint32_t* elem_strides = nullptr);
+              const uint32_t* box, const uint32_t* elem_strides = nullptr, int f32 = 0);
 bool tc_enabled();
 int tc_num_sms();
 

@@ -168,7 +168,7 @@ class GroupNormFn(Function):
         rstd = torch.empty_like(mean)
         a = torch.empty((B, C), dtype=torch.float32, device=dev)
         sh = torch.empty_like(a)
-        ws = torch.empty((B * C * 2,), dtype=torch.float64, device=dev)
+        ws = torch.empty((lib.query("groupnorm_ws_bytes", B, HW, C, dt(x)),), dtype=torch.uint8, device=dev)
         lib.call("groupnorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), ptr(a), ptr(sh), ptr(ws),
                  B, HW, C, groups, eps, 1 if silu else 0, dt(x), dt(y), stream())
         ctx.save_for_backward(x, mean, rstd, a, sh)
@@ -183,7 +183,7 @@ class GroupNormFn(Function):
         dy = _c(dy)
         dev = dy.device
         dx = torch.empty_like(x)
-        ws = torch.empty((B * C * 2,), dtype=torch.float64, device=dev)
+        ws = torch.empty((lib.query("groupnorm_ws_bytes", B, HW, C, dt(x)),), dtype=torch.uint8, device=dev)
         P = torch.empty((B * C,), dtype=torch.float32, device=dev)
         Q = torch.empty_like(P)
         want = ctx.needs_input_grad[1]
