@@ -450,7 +450,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                  dq_full = bar_base + 32;
   auto qdo_full = [&](int s) { return bar_base + 40 + 8u * s; };
   auto qdo_empty = [&](int s) { return bar_base + 56 + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 72;
+  const uint32_t sread = bar_base + 72;               // compute warps have read S^T_i out of TMEM
+  const uint32_t tmem_slot = bar_base + 80;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
   float* stat = reinterpret_cast<float*>(smem_raw + (stat_smem - smem_base));
 
@@ -462,6 +463,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (smem_base & 1023u) { printf("sidlsg attention bwd: dynamic smem not 1024-aligned\n"); __trap(); }
     mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    mbar_init(sread, 8);
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
@@ -502,21 +504,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
       const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
       mbar_wait(kv_full, 0);
-      for (int i = 0; i < TQ; ++i) {
-        const int st = i % QST;
-        mbar_wait(qdo_full(st), (i / QST) & 1);
-        tc_fence_after();
-        const uint32_t qb = q_smem + st * tile_bytes, dob = do_smem + st * tile_bytes;
+      auto issue_s = [&](int i) {          // S^T_i = K Q_i^T
+        const uint32_t qb = q_smem + (i % QST) * tile_bytes;
         for (int s = 0; s < dsteps; ++s) {
           const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
           tc_mma_bf16(st_tmem, make_desc(k_smem + off, 1024, 0), make_desc(qb + off, 1024, 0), idesc_s, s > 0);
         }
         tc_commit(s_full);
+      };
+      auto issue_dp = [&](int i) {         // dP^T_i = V dO_i^T
+        const uint32_t dob = do_smem + (i % QST) * tile_bytes;
         for (int s = 0; s < dsteps; ++s) {
           const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
           tc_mma_bf16(dp_tmem, make_desc(v_smem + off, 1024, 0), make_desc(dob + off, 1024, 0), idesc_s, s > 0);
         }
         tc_commit(dp_full);
+      };
+      // With a two-deep Q/dO ring the S^T of tile i+1 is issued as soon as the compute warps have READ S^T_i, so
+      // their exponentials for tile i+1 overlap the dV/dK/dQ MMAs of tile i.
+      const bool early = QST == 2;
+      mbar_wait(qdo_full(0), 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < TQ; ++i) {
+        const int st = i % QST;
+        const uint32_t qb = q_smem + st * tile_bytes, dob = do_smem + st * tile_bytes;
+        if (early && i + 1 < TQ) {
+          mbar_wait(sread, i & 1);
+          mbar_wait(qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
         for (int s = 0; s < 8; ++s) {      // reduction over the 128 query rows of this tile
@@ -535,6 +554,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tc_commit(qdo_empty(st));
         tc_commit(dq_full);
+        if (i + 1 < TQ) {
+          if (!early) {
+            mbar_wait(qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
+            tc_fence_after();
+            issue_s(i + 1);
+          }
+          issue_dp(i + 1);
+        }
       }
     }
   } else {
@@ -549,24 +576,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t c2 = pack2(c, c), scale2 = pack2(p.scale, p.scale);
     const uint32_t p_row = p_smem + row * 128, ds_row = ds_smem + row * 128;
     const int rx = row & 7;
+    // per-query statistics (negated, log2 domain for lse): tile i lives in stat[i & 1]; tile i+1 is fetched while
+    // tile i is being processed so the global-load latency never sits on the critical path
+    auto drain_dq = [&](int it) {
+      // drain dQ_i (TMEM lane = query row): stage the fp32 tile in smem, then ONE thread hands it to the TMA unit
+      // as a bulk reduce-add into dq_acc (the partials of the K/V tiles meet in L2, no per-thread atomics)
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      if (tid == 0) tma_wait_group_read0();        // the previous reduce has finished reading the staging tile
+      named_bar_sync(2, 256);
+      for (int blk = wg; blk * 16 < p.dpad; blk += 2) {
+        uint32_t r[16];
+        tmem_ld16_nowait(dq_tmem + lane_off + blk * 16, r);
+        tmem_wait_ld();
+        const uint32_t base = dq_stage + (blk >> 1) * AT_CHUNK + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(base + ((((blk & 1) * 4 + j) ^ rx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (tid == 0) {
+        for (int ch = 0; ch < dq_chunks; ++ch) tma_reduce_add_4d(&tmDQ, dq_stage + ch * AT_CHUNK, ch * 32, h, it * AT_BQ, b);
+        tma_commit_group();
+        if (p.stage_alias) tma_wait_group_read0();
+      }
+      if (p.stage_alias) named_bar_sync(2, 256);   // P^T / dS^T tiles may be rewritten only after the TMA read them
+    };
+    auto load_stat = [&](int i) -> float {
+      const int qi = i * AT_BQ + (tid & 127);
+      const long gi = ((long)b * p.H + h) * p.N + qi;
+      if (i >= TQ) return 0.f;
+      if (tid < 128) return qi < p.N ? -p.lse[gi] * 1.4426950408889634f : -INFINITY;
+      return qi < p.N ? -p.delta[gi] : 0.f;
+    };
+    stat[tid] = load_stat(0);
+    float stat_next = load_stat(1);
+    named_bar_sync(1, 256);
     for (int i = 0; i < TQ; ++i) {
       float* sb = stat + (i & 1) * 256;
-      {
-        const int qi = i * AT_BQ + (tid & 127);
-        const long gi = ((long)b * p.H + h) * p.N + qi;
-        if (tid < 128) sb[tid] = qi < p.N ? -p.lse[gi] * 1.4426950408889634f : -INFINITY;
-        else sb[tid] = qi < p.N ? -p.delta[gi] : 0.f;
-      }
-      named_bar_sync(1, 256);
       // sb holds the NEGATED statistics so they feed the packed FFMA2 / FADD2 directly
       const float* nlse2 = sb + wg * 64;
       const float* ndl = sb + 128 + wg * 64;
       uint64_t ps2[32];                      // P * scale for this thread's 64 query columns (fp32 pairs)
+      uint32_t pk[32];                       // P as packed bf16 pairs, stored once the previous tile's MMAs retired
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t r[32], pk[16];
+        uint32_t r[32];
         tmem_ld32_nowait(st_tmem + lane_off + wg * 64 + half * 32, r);
         tmem_wait_ld();
 #pragma unroll
@@ -577,16 +636,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           unpack2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), t2, t3);
           float p0 = ex2f(t0), p1 = ex2f(t1), p2 = ex2f(t2), p3 = ex2f(t3);
           if (!row_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-          pk[j >> 1] = pack_bf16(p0, p1);
-          pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+          pk[half * 16 + (j >> 1)] = pack_bf16(p0, p1);
+          pk[half * 16 + (j >> 1) + 1] = pack_bf16(p2, p3);
           ps2[half * 16 + (j >> 1)] = fmul2(pack2(p0, p1), scale2);
           ps2[half * 16 + (j >> 1) + 1] = fmul2(pack2(p2, p3), scale2);
         }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sread);     // S^T may be overwritten by the next tile's MMA
+      if (i > 0) drain_dq(i - 1);            // waits for tile i-1's MMAs: P^T / dS^T tiles and dQ are ours again
+      // publish the next tile's statistics (buffer (i+1)&1 was last read during tile i-1) and fetch tile i+2's
+      stat[((i + 1) & 1) * 256 + tid] = stat_next;
+      stat_next = load_stat(i + 2);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
-          st_shared_v4(p_row + wg * AT_CHUNK + (((half * 4 + qd) ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
-                       pk[4 * qd + 3]);
-      }
+          st_shared_v4(p_row + wg * AT_CHUNK + (((half * 4 + qd) ^ rx) << 4), pk[half * 16 + 4 * qd],
+                       pk[half * 16 + 4 * qd + 1], pk[half * 16 + 4 * qd + 2], pk[half * 16 + 4 * qd + 3]);
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
 #pragma unroll
@@ -614,31 +682,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // drain dQ_i (TMEM lane = query row): stage the fp32 tile in smem, then ONE thread hands it to the TMA unit
-      // as a bulk reduce-add into dq_acc (the partials of the K/V tiles meet in L2, no per-thread atomics)
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      if (tid == 0) tma_wait_group_read0();        // the previous reduce has finished reading the staging tile
-      named_bar_sync(2, 256);
-      for (int blk = wg; blk * 16 < p.dpad; blk += 2) {
-        uint32_t r[16];
-        tmem_ld16_nowait(dq_tmem + lane_off + blk * 16, r);
-        tmem_wait_ld();
-        const uint32_t base = dq_stage + (blk >> 1) * AT_CHUNK + row * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(base + ((((blk & 1) * 4 + j) ^ rx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      named_bar_sync(2, 256);
-      if (tid == 0) {
-        for (int ch = 0; ch < dq_chunks; ++ch) tma_reduce_add_4d(&tmDQ, dq_stage + ch * AT_CHUNK, ch * 32, h, i * AT_BQ, b);
-        tma_commit_group();
-        if (p.stage_alias) tma_wait_group_read0();
-      }
-      if (p.stage_alias) named_bar_sync(2, 256);   // P^T / dS^T tiles may be rewritten only after the TMA read them
+      named_bar_sync(1, 256);                 // statistics of tile i+1 are visible to every compute warp
     }
+    drain_dq(TQ - 1);
     if (tid == 0) tma_wait_group_read0();
     // the last dq_full commit covered every MMA: dV / dK accumulators are final. wg0 stores dV, wg1 stores dK.
     {
