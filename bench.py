@@ -182,7 +182,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a collective mismatch must fail fast instead of holding the GPUs for 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     cfg = getattr(S, args.model)
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(0)
@@ -286,12 +288,15 @@ def main():
 
     # ---- roofline pass: one more step with per-call CUDA events on the kernels' own stream ---------------------
     peaks = load_peaks()
-    if rank == 0 and not args.no_roofline:
-        timer = KernelTimer()
+    if not args.no_roofline:
+        # every rank runs the extra step (it contains the gradient allreduces); only rank 0 instruments it
+        timer = KernelTimer() if rank == 0 else None
         S.lib.timer = timer
         step_resident(0, args.warmup)
-        summ = timer.summary()
+        torch.cuda.synchronize()
         S.lib.timer = None
+    if rank == 0 and not args.no_roofline:
+        summ = timer.summary()
         kern = {}
         for key, d in summ.items():
             per = d["ms"] / max(d["launches"], 1)
