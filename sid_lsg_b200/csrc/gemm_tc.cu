@@ -11,8 +11,9 @@
 // (reference call sites: every Conv2d / Linear of the UNet behind training/sid_sd_util.py:184,245,263 and their
 // autograd, training/sid_training_loop.py:450,533).
 //
-// Roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias / timestep-row / residual -> global).
+// Roles (384 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> bias / timestep-row / residual -> global;
+// two warpgroups take alternate 32-column chunks of the tile).
 // 4-stage smem ring (128x64 A + up to 256x64 B, SWIZZLE_128B), two 256-column fp32 accumulators in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.  Tiles are 128 x block_n with a narrower last N tile
 // (UMMA N is a run-time field of the instruction descriptor), so N = 320 = 192 + 128 wastes nothing.
@@ -32,7 +33,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;          // 32 KB (max block_n)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 
 struct TcParams {
   int M, N;                 // output extent (rows, columns of the logical GEMM)
@@ -120,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -220,8 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (8 warps: two groups split the 32-column chunks of a tile) =====================
     const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int grp = (warp - 4) >> 2;     // column-chunk parity this warp handles
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -234,74 +236,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const long crow = (long)m * p.ldc + t.col0;
       const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long)(m / p.rows_per_vec) * p.N + t.col0 : nullptr;
-      for (int c = 0; c < t.n_valid; c += 16) {
-        float v[16];
-        __syncwarp();
-        tmem_ld16(taddr + c, v);          // warp-collective: every lane participates, stores are predicated
-        if (row_ok && has_work) {
-        const int nc = min(16, t.n_valid - c);
+      // fast path: whole 16-column groups, 16-byte aligned rows (every shape of the UNet)
+      const bool fast = ((t.n_valid & 15) == 0) && ((t.col0 & 15) == 0) &&
+                        (p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0)) &&
+                        ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
+                        (!p.res || (((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
+                        (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                        (!p.rowvec || (((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0)));
+      if (fast) {
+        for (int c = grp * 32; c < t.n_valid; c += 64) {
+          const bool two = c + 32 <= t.n_valid;     // 32 columns, or a 16-column tail
+          uint32_t r[32];
+          __syncwarp();
+          if (two) tmem_ld32_nowait(taddr + c, r);
+          else tmem_ld16_nowait(taddr + c, r);
+          tmem_wait_ld();
+          if (row_ok && has_work) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-        if (p.bias) {
+            for (int hblk = 0; hblk < 2; ++hblk) {
+              if (hblk == 1 && !two) break;
+              float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < nc) v[i] += __ldg(p.bias + t.col0 + c + i);
-        }
-        if (rv) {
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[hblk * 16 + i]) * p.alpha;
+              const int cc = c + hblk * 16;
+              if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < nc) v[i] += __ldg(rv + c + i);
-        }
-        if (p.out_f32) {
-          float* cp = reinterpret_cast<float*>(p.c) + crow + c;
-          if (p.res) {
-            const float* rp = reinterpret_cast<const float*>(p.res) + (long)m * p.ldr + t.col0 + c;
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + t.col0 + cc + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+              }
+              if (rv) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (i < nc) v[i] += rp[i];
-          }
-          if (p.atomic) {
-            if (nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + cc + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+              }
+              if (p.out_f32) {
+                float* cp = reinterpret_cast<float*>(p.c) + crow + cc;
+                if (p.res) {
+                  const float* rp = reinterpret_cast<const float*>(p.res) + (long)m * p.ldr + t.col0 + cc;
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + i), "f"(v[i]), "f"(v[i + 1]),
-                             "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
-            } else {
-              for (int i = 0; i < nc; ++i) atomicAdd(cp + i, v[i]);
+                  for (int i = 0; i < 16; i += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+                    v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+                  }
+                }
+                if (p.atomic) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + i), "f"(v[i]), "f"(v[i + 1]),
+                                 "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+              } else {
+                bf16* cp = reinterpret_cast<bf16*>(p.c) + crow + cc;
+                if (p.res) {
+                  const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (long)m * p.ldr + t.col0 + cc;
+                  const uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
+                  const __nv_bfloat162* e0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                  const __nv_bfloat162* e1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    v[2 * i] += __low2float(e0[i]); v[2 * i + 1] += __high2float(e0[i]);
+                    v[8 + 2 * i] += __low2float(e1[i]); v[8 + 2 * i + 1] += __high2float(e1[i]);
+                  }
+                }
+                uint4 o0, o1;
+                __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+                __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                  h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                }
+                *reinterpret_cast<uint4*>(cp) = o0;
+                *reinterpret_cast<uint4*>(cp + 8) = o1;
+              }
             }
-          } else if (nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            for (int i = 0; i < nc; ++i) cp[i] = v[i];
-          }
-        } else {
-          bf16* cp = reinterpret_cast<bf16*>(p.c) + crow + c;
-          const bool vec = nc == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
-          if (p.res) {
-            const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (long)m * p.ldr + t.col0 + c;
-            if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-              uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
-              const bf16* e0 = reinterpret_cast<const bf16*>(&r0);
-              const bf16* e1 = reinterpret_cast<const bf16*>(&r1);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { v[i] += __bfloat162float(e0[i]); v[8 + i] += __bfloat162float(e1[i]); }
-            } else {
-              for (int i = 0; i < nc; ++i) v[i] += __bfloat162float(rp[i]);
-            }
-          }
-          if (vec) {
-            uint4 o0, o1;
-            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-            }
-            *reinterpret_cast<uint4*>(cp) = o0;
-            *reinterpret_cast<uint4*>(cp + 8) = o1;
-          } else {
-            for (int i = 0; i < nc; ++i) cp[i] = __float2bfloat16_rn(v[i]);
           }
         }
+      } else if (grp == 0) {
+        // generic path (odd widths / unaligned rows): scalar tails, one warpgroup
+        for (int c = 0; c < t.n_valid; c += 16) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(taddr + c, v);
+          if (row_ok && has_work) {
+            const int nc = min(16, t.n_valid - c);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < nc) {
+                float x = v[i] * p.alpha;
+                if (p.bias) x += __ldg(p.bias + t.col0 + c + i);
+                if (rv) x += __ldg(rv + c + i);
+                if (p.out_f32) {
+                  float* cp = reinterpret_cast<float*>(p.c) + crow + c + i;
+                  if (p.res) x += reinterpret_cast<const float*>(p.res)[(long)m * p.ldr + t.col0 + c + i];
+                  if (p.atomic) atomicAdd(cp, x);
+                  else *cp = x;
+                } else {
+                  if (p.res) x += __bfloat162float(reinterpret_cast<const bf16*>(p.res)[(long)m * p.ldr + t.col0 + c + i]);
+                  reinterpret_cast<bf16*>(p.c)[crow + c + i] = __float2bfloat16_rn(x);
+                }
+              }
+            }
+          }
         }
       }
       tc_fence_before();
