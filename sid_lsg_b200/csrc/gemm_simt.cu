@@ -353,6 +353,13 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
 int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
                          int Cout, long dw_sco, long dw_stap, long dw_sci, int stride, int up, int accumulate,
                          int in_dtype, cudaStream_t st);
+// direct kernels for the 4-channel convolutions (conv_small.cu)
+int conv_small_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec, int B,
+                   int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride, int up,
+                   int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st);
+int conv_small_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
+                         int Cout, long dw_sco, long dw_stap, long dw_sci, int stride, int up, int accumulate,
+                         int in_dtype, cudaStream_t st);
 
 }  // namespace sidlsg
 
@@ -412,6 +419,9 @@ extern "C" int sidlsg_conv3x3(const void* x, const void* w, void* y, const float
     int r = tc_conv3x3_try(x, w, y, bias, res, rowvec, B, Hi, Wi, Kc, Ho, Wo, N, w_sn, w_stap, w_sk, stride, up,
                            transposed, flip, accumulate, in_dtype, out_dtype, st);
     if (r != 0) return r < 0 ? r : SIDLSG_OK;
+    r = conv_small_try(x, w, y, bias, res, rowvec, B, Hi, Wi, Kc, Ho, Wo, N, w_sn, w_stap, w_sk, stride, up, transposed,
+                       flip, accumulate, in_dtype, out_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
   }
   int M = B * Ho * Wo, K = 9 * Kc;
   ConvGeom g{B, Hi, Wi, Kc, Ho, Wo, stride, up, transposed};
@@ -439,6 +449,9 @@ extern "C" int sidlsg_conv3x3_wgrad(const void* x, const void* dy, float* dw, in
   if (B > 0) {
     int r = tc_conv3x3_wgrad_try(x, dy, dw, B, Hi, Wi, Cin, Ho, Wo, Cout, dw_sco, dw_stap, dw_sci, stride, up,
                                  accumulate, in_dtype, st);
+    if (r != 0) return r < 0 ? r : SIDLSG_OK;
+    r = conv_small_wgrad_try(x, dy, dw, B, Hi, Wi, Cin, Ho, Wo, Cout, dw_sco, dw_stap, dw_sci, stride, up, accumulate,
+                             in_dtype, st);
     if (r != 0) return r < 0 ? r : SIDLSG_OK;
   }
   int M = Cout, N = 9 * Cin, K = B * Ho * Wo;
