@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
+    ap.add_argument("--shapes", default=None, help="write the per-shape kernel table of the roofline step to this file")
     return ap.parse_args()
 
 
@@ -323,6 +324,13 @@ def main():
                             "algorithmic_flop_per_launch": work / max(n, 1), "share_of_step": round(ms / ms_step, 4),
                             "measured_on": "1 instrumented step right after the timed region (per-call CUDA events on the launch stream)"}
         line["kernels"] = kern
+        if args.shapes:
+            with open(args.shapes, "w") as f:
+                for d in timer.by_shape():
+                    rate = d["work"] / max(d["ms"], 1e-9) / (1e9 if d["unit"] == "flop" else 1e6)
+                    f.write("%-16s tc=%d %-44s n=%-5d ms=%9.3f avg_us=%8.1f %8.1f %s\n" % (
+                        d["name"], d["tc"], d["shape"], d["launches"], d["ms"], 1e3 * d["ms"] / d["launches"], rate,
+                        "TFLOP/s" if d["unit"] == "flop" else "GB/s"))
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -91,9 +91,10 @@ int sidlsg_layernorm_bwd(const void* dy, const void* x, const float* gamma, cons
 
 /* ---- attention pieces of the fp32-exact path (scores materialised per batch chunk) -----------------------
  * ref: diffusers Attention: softmax(Q K^T / sqrt(d)) V, no mask (enable_xformers / SDPA are numerically
- * equivalent reorderings, training/sid_sd_util.py:102-113). S and dP are fp32; P and dS are `dtype`. */
-int sidlsg_softmax_fwd(const float* S, void* P, long rows, int cols, float scale, int dtype, void* stream);
-int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int cols, float scale, int dtype,
+ * equivalent reorderings, training/sid_sd_util.py:102-113). S and dP are fp32; P and dS are `dtype`; ld = row
+ * stride in elements of all matrices (>= cols; padded to a multiple of 8 so bf16 P / dS are valid TMA operands). */
+int sidlsg_softmax_fwd(const float* S, void* P, long rows, int cols, long ld, float scale, int dtype, void* stream);
+int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int cols, long ld, float scale, int dtype,
                        void* stream);
 
 /* Flash attention on tcgen05/TMEM/TMA (bf16): o = softmax(q k^T / sqrt(d)) v per (batch, head) with no score

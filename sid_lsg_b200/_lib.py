@@ -83,7 +83,7 @@ class _Lib:
             st = self._fns["sidlsg_" + name](*args)
             ev1.record()
             path = self._fns["sidlsg_last_path"]() if name in ("gemm", "conv3x3", "conv3x3_wgrad") else 1
-            timer.records.append((name, path, timer.work[name](args), ev0, ev1))
+            timer.records.append((name, path, timer.work[name](args), ev0, ev1, timer.shape_of(name, args)))
         else:
             st = self._fns["sidlsg_" + name](*args)
         if st != 0:
@@ -129,11 +129,40 @@ class KernelTimer:
                      "lsg_loss": lsg}
         self.records = []
 
+    @staticmethod
+    def shape_of(name, a):
+        """short shape tag of a timed call (per-shape table of bench.py --shapes)."""
+        if name == "gemm":      # M,N,K, batches, operand majors, accumulate
+            return "M%d N%d K%d nb%d %s%s acc%d" % (a[23], a[24], a[25], a[26] * a[27], "k" if a[2] == 1 else "m",
+                                                    "k" if a[7] == 1 else "n", a[22])
+        if name == "conv3x3":   # B,Hi,Wi,Kc,Ho,Wo,N ... stride, flip
+            return "B%d H%d C%d->%d s%d%s" % (a[6], a[7], a[9], a[12], a[16], " dgrad" if a[19] else "")
+        if name == "conv3x3_wgrad":
+            return "B%d H%d C%d->%d s%d" % (a[3], a[4], a[6], a[9], a[13])
+        if name == "attention_fwd":
+            return "B%d N%d M%d H%d d%d" % tuple(a[5:10])
+        if name == "attention_bwd":
+            return "B%d N%d M%d H%d d%d" % tuple(a[-6:-1])
+        if name in ("groupnorm_fwd", "groupnorm_bwd"):
+            return "B%d HW%d C%d" % ((a[9], a[10], a[11]) if name == "groupnorm_fwd" else (a[13], a[14], a[15]))
+        return ""
+
+    def by_shape(self):
+        """-> list of dict(name, path, shape, launches, ms, work, unit) sorted by time."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, path, (unit, work), ev0, ev1, shape in self.records:
+            d = out.setdefault((name, path, shape), dict(name=name, tc=path, shape=shape, launches=0, ms=0.0, work=0.0, unit=unit))
+            d["launches"] += 1
+            d["ms"] += ev0.elapsed_time(ev1)
+            d["work"] += work
+        return sorted(out.values(), key=lambda d: -d["ms"])
+
     def summary(self):
         """-> {key: dict(launches, ms, work, unit)}; key = name or name+'[simt]' for CUDA-core GEMM/conv calls."""
         torch.cuda.synchronize()
         out = {}
-        for name, path, (unit, work), ev0, ev1 in self.records:
+        for name, path, (unit, work), ev0, ev1, _shape in self.records:
             key = name if path else name + "[simt]"
             d = out.setdefault(key, dict(launches=0, ms=0.0, work=0.0, unit=unit))
             d["launches"] += 1

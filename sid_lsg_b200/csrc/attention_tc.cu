@@ -604,14 +604,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (p.stage_alias) named_bar_sync(2, 256);   // P^T / dS^T tiles may be rewritten only after the TMA read them
     };
+    // raw global value of this thread's statistic (lse for tid < 128, delta otherwise); the negation / log2 scaling
+    // is applied when the value is published to smem one iteration later, so nothing depends on the load before then
     auto load_stat = [&](int i) -> float {
       const int qi = i * AT_BQ + (tid & 127);
+      if (i >= TQ || qi >= p.N) return tid < 128 ? INFINITY : 0.f;
       const long gi = ((long)b * p.H + h) * p.N + qi;
-      if (i >= TQ) return 0.f;
-      if (tid < 128) return qi < p.N ? -p.lse[gi] * 1.4426950408889634f : -INFINITY;
-      return qi < p.N ? -p.delta[gi] : 0.f;
+      return tid < 128 ? p.lse[gi] : p.delta[gi];
     };
-    stat[tid] = load_stat(0);
+    auto stat_value = [&](float raw) -> float { return tid < 128 ? raw * -1.4426950408889634f : -raw; };
+    stat[tid] = stat_value(load_stat(0));
     float stat_next = load_stat(1);
     named_bar_sync(1, 256);
     for (int i = 0; i < TQ; ++i) {
@@ -627,10 +629,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
         tmem_ld32_nowait(st_tmem + lane_off + wg * 64 + half * 32, r);
+        float4 nlv[8];                        // statistics fetched while the TMEM load is in flight
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nlv[j] = *reinterpret_cast<const float4*>(nlse2 + half * 32 + 4 * j);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 nl = *reinterpret_cast<const float4*>(nlse2 + half * 32 + j);
+          const float4 nl = nlv[j >> 2];
           float t0, t1, t2, t3;
           unpack2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(nl.x, nl.y)), t0, t1);
           unpack2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), t2, t3);
@@ -647,7 +652,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(sread);     // S^T may be overwritten by the next tile's MMA
       if (i > 0) drain_dq(i - 1);            // waits for tile i-1's MMAs: P^T / dS^T tiles and dQ are ours again
       // publish the next tile's statistics (buffer (i+1)&1 was last read during tile i-1) and fetch tile i+2's
-      stat[((i + 1) & 1) * 256 + tid] = stat_next;
+      stat[((i + 1) & 1) * 256 + tid] = stat_value(stat_next);
       stat_next = load_stat(i + 2);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
@@ -661,10 +666,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32], dsk[16];
         tmem_ld32_nowait(dp_tmem + lane_off + wg * 64 + half * 32, r);
+        float4 ndv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ndv[j] = *reinterpret_cast<const float4*>(ndl + half * 32 + 4 * j);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 nd = *reinterpret_cast<const float4*>(ndl + half * 32 + j);
+          const float4 nd = ndv[j >> 2];
           float d0, d1, d2, d3;
           unpack2(fmul2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(nd.x, nd.y)),
                         ps2[half * 16 + (j >> 1)]), d0, d1);

@@ -281,27 +281,42 @@ skinny_nt_kernel(const float* __restrict__ A, long a_sm, const float* __restrict
   }
 }
 
-// C[m][n] = sum_k A[m][k] B[k][n]   (B n-contiguous): one thread per column n, every k row read coalesced
+// C[m][n] (+)= sum_k A[m][k] B[k][n]   (B n-contiguous): one thread per column n, blockIdx.y = a slab of SK_KSLAB
+// reduction rows (every k row of B is read once, coalesced); slabs meet in C through fp32 atomics, so the
+// whole matrix is spread over N/128 x K/SK_KSLAB CTAs instead of N/128 (the data-gradient of the timestep
+// projections has N = 1280: ten CTAs streamed a 6.5 MB weight matrix before).  C must be zeroed by the caller
+// when it is not an accumulation (skinny_try does).
+constexpr int SK_KSLAB = 32;
 __global__ void __launch_bounds__(128)
 skinny_nn_kernel(const float* __restrict__ A, long a_sm, long a_sk, const float* __restrict__ Bm, long b_sk,
-                 float* __restrict__ C, long ldc, int M, int N, int K, float alpha, int accumulate) {
+                 float* __restrict__ C, long ldc, int M, int N, int K, float alpha) {
+  __shared__ float As[SK_KSLAB][SK_M];
   const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * SK_KSLAB, k1 = min(K, k0 + SK_KSLAB);
+  for (int i = threadIdx.x; i < SK_KSLAB * SK_M; i += 128) {
+    const int kk = i / SK_M, m = i - kk * SK_M;
+    As[kk][m] = (m < M && k0 + kk < k1) ? A[(long)m * a_sm + (long)(k0 + kk) * a_sk] : 0.f;
+  }
+  __syncthreads();
   if (n >= N) return;
   float acc[SK_M];
 #pragma unroll
   for (int m = 0; m < SK_M; ++m) acc[m] = 0.f;
-  for (int k = 0; k < K; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const float bv = Bm[(long)k * b_sk + n];
+    const float4* ar = reinterpret_cast<const float4*>(As[k - k0]);
 #pragma unroll
-    for (int m = 0; m < SK_M; ++m)
-      if (m < M) acc[m] = fmaf(A[(long)m * a_sm + (long)k * a_sk], bv, acc[m]);
+    for (int m4 = 0; m4 < SK_M / 4; ++m4) {
+      const float4 a4 = ar[m4];
+      acc[4 * m4] = fmaf(a4.x, bv, acc[4 * m4]);
+      acc[4 * m4 + 1] = fmaf(a4.y, bv, acc[4 * m4 + 1]);
+      acc[4 * m4 + 2] = fmaf(a4.z, bv, acc[4 * m4 + 2]);
+      acc[4 * m4 + 3] = fmaf(a4.w, bv, acc[4 * m4 + 3]);
+    }
   }
 #pragma unroll
   for (int m = 0; m < SK_M; ++m)
-    if (m < M) {
-      float* dst = C + (long)m * ldc + n;
-      *dst = accumulate ? *dst + alpha * acc[m] : alpha * acc[m];
-    }
+    if (m < M) atomicAdd(C + (long)m * ldc + n, alpha * acc[m]);
 }
 
 // C[m][n] (+)= sum_{k < K <= 32} A[k][m] B[k][n]   (both read along their contiguous dimension): weight gradients
@@ -331,9 +346,10 @@ static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long
     return check_launch("skinny_nt") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
   }
   if (M <= 4 * SK_M && b_sn == 1 && !bias && !res) {
+    if (!accumulate) cudaMemset2DAsync(c, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
     for (int m0 = 0; m0 < M; m0 += SK_M)
-      skinny_nn_kernel<<<cdiv(N, 128), 128, 0, st>>>(a + m0 * a_sm, a_sm, a_sk, b, b_sk, c + m0 * ldc, ldc,
-                                                      min(SK_M, M - m0), N, K, alpha, accumulate);
+      skinny_nn_kernel<<<dim3(cdiv(N, 128), cdiv(K, SK_KSLAB)), 128, 0, st>>>(
+          a + m0 * a_sm, a_sm, a_sk, b, b_sk, c + m0 * ldc, ldc, min(SK_M, M - m0), N, K, alpha);
     return check_launch("skinny_nn") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
   }
   if (K <= 4 * SK_M && a_sm == 1 && b_sn == 1 && !bias && !res && M <= 65535) {
@@ -344,9 +360,10 @@ static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long
 }
 
 // tensor-core (tcgen05) paths of gemm_tc.cu: return 1 = handled, 0 = shape not eligible, <0 = error
-int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, long b_sk, void* c, long ldc,
-                const float* bias, const void* res, long ldr, const float* rowvec, int rows_per_vec, float alpha,
-                int accumulate, int M, int N, int K, int in_dtype, int out_dtype, cudaStream_t st);
+int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, const void* b, long b_sn, long b_sk,
+                long b_sb1, long b_sb2, void* c, long ldc, long c_sb1, long c_sb2, const float* bias, const void* res,
+                long ldr, const float* rowvec, int rows_per_vec, float alpha, int accumulate, int M, int N, int K,
+                int nb1, int nb2, int in_dtype, int out_dtype, cudaStream_t st);
 int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec,
                    int B, int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride,
                    int up, int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st);
@@ -374,9 +391,9 @@ extern "C" int sidlsg_gemm(const void* a, long a_sm, long a_sk, long a_sb1, long
   if (M < 0 || N < 0 || K < 0 || nb1 < 1 || nb2 < 1) { set_error("sidlsg_gemm: bad shape"); return SIDLSG_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   int nbatch = nb1 * nb2;
-  if (nbatch == 1 && M > 0 && N > 0 && K > 0) {
-    int r = tc_gemm_try(a, a_sm, a_sk, b, b_sn, b_sk, c, ldc, bias, res, ldr, rowvec, rows_per_vec, alpha, accumulate,
-                        M, N, K, in_dtype, out_dtype, st);
+  if (M > 0 && N > 0 && K > 0) {
+    int r = tc_gemm_try(a, a_sm, a_sk, a_sb1, a_sb2, b, b_sn, b_sk, b_sb1, b_sb2, c, ldc, c_sb1, c_sb2, bias, res, ldr,
+                        rowvec, rows_per_vec, alpha, accumulate, M, N, K, nb1, nb2, in_dtype, out_dtype, st);
     if (r != 0) return r < 0 ? r : SIDLSG_OK;
   }
   if (nbatch == 1 && in_dtype == SIDLSG_F32 && out_dtype == SIDLSG_F32 && M > 0 && N > 0 && K > 0) {

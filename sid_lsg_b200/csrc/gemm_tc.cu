@@ -59,6 +59,10 @@ struct TcParams {
   int rows_per_vec;
   float alpha;
   int atomic;               // fp32 red.add (split-K / gradient accumulation)
+  // batched dense GEMMs (attention score / value contractions per (batch, head)): 4-D operand maps
+  // (inner, outer, nb2, nb1); tile index = ((batch * m_tiles) + m) * n_tiles + n
+  int batched, nb2;
+  long c_sb1, c_sb2;
 };
 
 // 16 consecutive fp32 columns of this thread's TMEM lane
@@ -71,7 +75,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 struct TileInfo {
-  int m0, n_in, col0, n_valid, tap, kb0, kb1;
+  int m0, n_in, col0, n_valid, tap, kb0, kb1, b1, b2;
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
@@ -80,6 +84,13 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   int r = tile / p.splits;
   int n_blk = r % p.n_tiles;
   int m_blk = r / p.n_tiles;
+  t.b1 = t.b2 = 0;
+  if (p.batched) {
+    const int bidx = m_blk / p.m_tiles;
+    m_blk -= bidx * p.m_tiles;
+    t.b1 = bidx / p.nb2;
+    t.b2 = bidx - t.b1 * p.nb2;
+  }
   t.m0 = m_blk * TC_BM;
   if (p.b_mode == B_CONV) {
     t.tap = n_blk / p.n_tiles_per_tap;
@@ -113,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -156,7 +167,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int tap = 0, c0 = kb * TC_BK;
           if (p.a_mode == A_CONV || p.b_mode == B_W3D) { tap = kb / p.cchunks; c0 = (kb - tap * p.cchunks) * TC_BK; }
           // ---- A ----
-          if (p.a_mode == A_K2D) {
+          if (p.batched) {
+            if (p.a_mode == A_K2D) {
+              tma_load_4d(&tmA, fb, sa, kb * TC_BK, t.m0, t.b2, t.b1);
+            } else {
+              tma_load_4d(&tmA, fb, sa, t.m0, kb * TC_BK, t.b2, t.b1);
+              tma_load_4d(&tmA, fb, sa + 8192, t.m0 + 64, kb * TC_BK, t.b2, t.b1);
+            }
+          } else if (p.a_mode == A_K2D) {
             tma_load_2d(&tmA, fb, sa, kb * TC_BK, t.m0);
           } else if (p.a_mode == A_MN2D) {
             tma_load_2d(&tmA, fb, sa, t.m0, kb * TC_BK);
@@ -167,7 +185,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(&tmA, fb, sa, c0, ox, ah0 * p.cstride + oy, ab0);
           }
           // ---- B ----
-          if (p.b_mode == B_K2D) {
+          if (p.batched) {
+            if (p.b_mode == B_K2D) {
+              tma_load_4d(&tmB, fb, sb, kb * TC_BK, t.n_in, t.b2, t.b1);
+            } else {
+              for (int j = 0; j < b_boxes; ++j) tma_load_4d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, kb * TC_BK, t.b2, t.b1);
+            }
+          } else if (p.b_mode == B_K2D) {
             tma_load_2d(&tmB, fb, sb, kb * TC_BK, t.n_in);
           } else if (p.b_mode == B_MN2D) {
             for (int j = 0; j < b_boxes; ++j) tma_load_2d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, kb * TC_BK);
@@ -234,12 +258,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = m < p.M;
       const bool has_work = t.kb1 > t.kb0;
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      const long crow = (long)m * p.ldc + t.col0;
+      const long crow = (long)m * p.ldc + t.col0 + t.b1 * p.c_sb1 + t.b2 * p.c_sb2;
       const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long)(m / p.rows_per_vec) * p.N + t.col0 : nullptr;
       // fast path: whole 16-column groups, 16-byte aligned rows (every shape of the UNet)
       const bool fast = ((t.n_valid & 15) == 0) && ((t.col0 & 15) == 0) &&
                         (p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0)) &&
                         ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
+                        (((p.c_sb1 | p.c_sb2) & (p.out_f32 ? 3 : 7)) == 0) &&
                         (!p.res || (((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
                         (!p.rowvec || (((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0)));
@@ -454,7 +479,7 @@ thread_local int g_last_path = 0;   // 1 = the last GEMM/conv entry point of thi
 extern long g_simt_launches;
 
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
-  long tiles = (long)p.m_tiles * p.n_tiles * p.splits;
+  long tiles = (long)p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
   if (tiles <= 0) return SIDLSG_OK;
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
   g_last_path = 1;
@@ -475,11 +500,14 @@ static int pick_splits(long tiles, int kb_total) {
 
 // Returns 1 if handled on the tensor cores, 0 if the shape is not eligible (caller falls back to the CUDA-core
 // kernel of gemm_simt.cu, which is the same arithmetic), <0 on error.
-int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, long b_sk, void* c, long ldc,
-                const float* bias, const void* res, long ldr, const float* rowvec, int rows_per_vec, float alpha,
-                int accumulate, int M, int N, int K, int in_dtype, int out_dtype, cudaStream_t st) {
+// nb1 x nb2 independent problems (batch strides in elements; 1 x 1 = plain GEMM).
+int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, const void* b, long b_sn, long b_sk,
+                long b_sb1, long b_sb2, void* c, long ldc, long c_sb1, long c_sb2, const float* bias, const void* res,
+                long ldr, const float* rowvec, int rows_per_vec, float alpha, int accumulate, int M, int N, int K,
+                int nb1, int nb2, int in_dtype, int out_dtype, cudaStream_t st) {
   if (!tc_enabled() || in_dtype != SIDLSG_BF16) return 0;
-  if (M < 64 || N < 16 || K < 64 || (N % 8)) return 0;
+  const int nbatch = nb1 * nb2;
+  if (M < 64 || N < 16 || K < 64) return 0;
   if (accumulate == 1) return 0;
   if (accumulate == 2 && out_dtype != SIDLSG_F32) return 0;
   const bool a_k = a_sk == 1, a_mn = a_sm == 1 && !a_k;
@@ -487,9 +515,12 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, l
   if (!(a_k || a_mn) || !(b_k || b_mn)) return 0;
   const long lda = a_k ? a_sm : a_sk, ldb = b_k ? b_sn : b_sk;
   if ((lda % 8) || (ldb % 8) || !aligned16(a) || !aligned16(b)) return 0;
-  if (a_mn && (M % 8)) return 0;
-  if (b_mn && (N % 8)) return 0;
-  if (out_dtype == SIDLSG_BF16 && (ldc % 8)) return 0;
+  if (out_dtype == SIDLSG_BF16 && ((ldc % 8) || (N % 8))) return 0;
+  if (nbatch > 1) {
+    if (accumulate || bias || res || rowvec) return 0;
+    if ((a_sb1 % 8) || (a_sb2 % 8) || (b_sb1 % 8) || (b_sb2 % 8)) return 0;
+    if ((long)nbatch * ((M + TC_BM - 1) / TC_BM) * N > (1L << 30)) return 0;
+  }
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -504,26 +535,19 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, const void* b, long b_sn, l
   p.c = c; p.ldc = ldc; p.out_f32 = out_dtype == SIDLSG_F32;
   p.bias = bias; p.res = res; p.ldr = ldr; p.rowvec = rowvec; p.rows_per_vec = rows_per_vec > 0 ? rows_per_vec : 1;
   p.alpha = alpha; p.atomic = accumulate == 2;
+  p.batched = nbatch > 1 ? nbatch : 0; p.nb2 = nb2; p.c_sb1 = c_sb1; p.c_sb2 = c_sb2;
 
   CUtensorMap ta, tb;
-  if (a_k) {
-    uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
-    uint32_t bx[2] = {64, 128};
-    if (!make_map(&ta, a, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
-  } else {
-    uint64_t d[2] = {(uint64_t)M, (uint64_t)K}, s[1] = {(uint64_t)lda * 2};
-    uint32_t bx[2] = {64, 64};
-    if (!make_map(&ta, a, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
-  }
-  if (b_k) {
-    uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
-    uint32_t bx[2] = {64, (uint32_t)p.block_n};
-    if (!make_map(&tb, b, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
-  } else {
-    uint64_t d[2] = {(uint64_t)N, (uint64_t)K}, s[1] = {(uint64_t)ldb * 2};
-    uint32_t bx[2] = {64, 64};
-    if (!make_map(&tb, b, 2, d, s, bx)) return SIDLSG_ERR_CUDA;
-  }
+  // operand maps: (inner, outer[, nb2, nb1]); a batch dimension of extent 1 gets a harmless 16-byte-multiple stride
+  auto dense_map = [&](CUtensorMap* m, const void* base, bool kmajor, int rows, long ld, long sb1, long sb2,
+                       uint32_t box_rows) -> bool {
+    uint64_t d[4] = {kmajor ? (uint64_t)K : (uint64_t)rows, kmajor ? (uint64_t)rows : (uint64_t)K, (uint64_t)nb2, (uint64_t)nb1};
+    uint64_t s[3] = {(uint64_t)ld * 2, (uint64_t)(nb2 > 1 ? sb2 : ld) * 2, (uint64_t)(nb1 > 1 ? sb1 : ld) * 2};
+    uint32_t bx[4] = {64, kmajor ? box_rows : 64u, 1, 1};
+    return make_map(m, base, nbatch > 1 ? 4 : 2, d, s, bx);
+  };
+  if (!dense_map(&ta, a, a_k, M, lda, a_sb1, a_sb2, 128)) return SIDLSG_ERR_CUDA;
+  if (!dense_map(&tb, b, b_k, N, ldb, b_sb1, b_sb2, (uint32_t)p.block_n)) return SIDLSG_ERR_CUDA;
   int r = launch_tc(ta, tb, p, st);
   return r == SIDLSG_OK ? 1 : r;
 }

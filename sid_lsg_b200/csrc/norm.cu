@@ -231,18 +231,20 @@ gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restri
   }
 }
 
-// dgamma[c] (+)= sum_{b,chunk} partial.y ; dbeta[c] (+)= sum partial.x
+// dgamma[c] += sum_{b,chunk} partial.y ; dbeta[c] += sum partial.x.  blockIdx.y strides over the (b, chunk) rows so
+// the reduction is spread over SMs; slices meet through fp32 atomics (the caller zeroes dgamma/dbeta first when
+// it does not accumulate).
 __global__ void gn_bwd_param_kernel(const float2* __restrict__ partial, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int B, int C, int chunks, int accumulate) {
+                                    float* __restrict__ dbeta, int rows, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double s = 0, q = 0;
-  for (int i = 0; i < B * chunks; ++i) {
+  float s = 0.f, q = 0.f;
+  for (int i = blockIdx.y; i < rows; i += gridDim.y) {
     const float2 v = partial[(long)i * C + c];
     s += v.x; q += v.y;
   }
-  if (accumulate) { dgamma[c] += (float)q; dbeta[c] += (float)s; }
-  else { dgamma[c] = (float)q; dbeta[c] = (float)s; }
+  atomicAdd(dgamma + c, q);
+  atomicAdd(dbeta + c, s);
 }
 
 template <class T, int VEC>
@@ -427,7 +429,15 @@ extern "C" int sidlsg_groupnorm_bwd(const void* dy, const void* x, const float* 
   else
     gn_bwd_stats_kernel<bf16, 8><<<grid, block, sm, st>>>((const bf16*)dy, (const bf16*)x, a, sh, mean, rstd, part, HW, C, G, C / 8, g.iters, g.rows_per_chunk, silu);
   gn_bwd_finalize_kernel<<<cdiv((long)B * G * 32, 256), 256, 0, st>>>(part, gamma, mean, rstd, P, Q, B, C, G, HW, g.chunks);
-  if (dgamma && dbeta) gn_bwd_param_kernel<<<cdiv(C, 128), 128, 0, st>>>(part, dgamma, dbeta, B, C, g.chunks, accumulate);
+  if (dgamma && dbeta) {
+    if (!accumulate) {
+      cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
+      cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
+    }
+    const int rows = B * g.chunks;
+    const int ysplit = rows < 64 ? rows : 64;
+    gn_bwd_param_kernel<<<dim3(cdiv(C, 128), ysplit), 128, 0, st>>>(part, dgamma, dbeta, rows, C);
+  }
   if (dtype == SIDLSG_F32)
     gn_bwd_apply_kernel<float, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)dy, (const float*)x, a, sh, P, Q, (float*)dx, total / 4, HW * C, C, silu);
   else

@@ -8,14 +8,15 @@ namespace sidlsg {
 // P = softmax(scale * S) row-wise, in place allowed (P may alias S)
 template <class TI, class T>
 __global__ void __launch_bounds__(256)
-softmax_fwd_kernel(const TI* __restrict__ S, T* __restrict__ P, long rows, int cols, float scale, int warp_per_row) {
+softmax_fwd_kernel(const TI* __restrict__ S, T* __restrict__ P, long rows, int cols, long ld, float scale,
+                   int warp_per_row) {
   __shared__ float sh[33];
   if (warp_per_row) {
     const int lane = threadIdx.x & 31;
     long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
-    const TI* s = S + r * cols;
-    T* p = P + r * cols;
+    const TI* s = S + r * ld;
+    T* p = P + r * ld;
     float mx = -INFINITY;
     for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, to_f(s[c]) * scale);
     mx = warp_max(mx);
@@ -26,8 +27,8 @@ softmax_fwd_kernel(const TI* __restrict__ S, T* __restrict__ P, long rows, int c
     for (int c = lane; c < cols; c += 32) p[c] = from_f<T>(expf(to_f(s[c]) * scale - mx) * inv);
   } else {
     long r = blockIdx.x;
-    const TI* s = S + r * cols;
-    T* p = P + r * cols;
+    const TI* s = S + r * ld;
+    T* p = P + r * ld;
     float mx = -INFINITY;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, to_f(s[c]) * scale);
     mx = warp_max(mx);
@@ -56,24 +57,24 @@ softmax_fwd_kernel(const TI* __restrict__ S, T* __restrict__ P, long rows, int c
 template <class TI, class T>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const T* __restrict__ P, const TI* __restrict__ dP, T* __restrict__ dS, long rows, int cols,
-                   float scale, int warp_per_row) {
+                   long ld, float scale, int warp_per_row) {
   __shared__ float sh[33];
   if (warp_per_row) {
     const int lane = threadIdx.x & 31;
     long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
-    const T* p = P + r * cols;
-    const TI* dp = dP + r * cols;
-    T* ds = dS + r * cols;
+    const T* p = P + r * ld;
+    const TI* dp = dP + r * ld;
+    T* ds = dS + r * ld;
     float dot = 0.f;
     for (int c = lane; c < cols; c += 32) dot = fmaf(to_f(p[c]), to_f(dp[c]), dot);
     dot = warp_sum(dot);
     for (int c = lane; c < cols; c += 32) ds[c] = from_f<T>(scale * to_f(p[c]) * (to_f(dp[c]) - dot));
   } else {
     long r = blockIdx.x;
-    const T* p = P + r * cols;
-    const TI* dp = dP + r * cols;
-    T* ds = dS + r * cols;
+    const T* p = P + r * ld;
+    const TI* dp = dP + r * ld;
+    T* ds = dS + r * ld;
     float dot = 0.f;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) dot = fmaf(to_f(p[c]), to_f(dp[c]), dot);
     dot = block_sum(dot, sh);
@@ -86,19 +87,23 @@ softmax_bwd_kernel(const T* __restrict__ P, const TI* __restrict__ dP, T* __rest
 using namespace sidlsg;
 
 // S / dP are fp32 (the score GEMMs always accumulate and store fp32); P / dS are in `dtype` (fp32 or bf16)
-// P may alias S and dS may alias dP only when dtype is fp32.
-extern "C" int sidlsg_softmax_fwd(const float* S, void* P, long rows, int cols, float scale, int dtype, void* stream) {
-  if (rows == 0 || cols == 0) return SIDLSG_OK;
-  int wpr = cols <= 256;
-  long blocks = wpr ? (rows + 7) / 8 : rows;
-  SID_DISPATCH_DTYPE(dtype, T, (softmax_fwd_kernel<float, T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, (T*)P, rows, cols, scale, wpr)));
-  return check_launch("softmax_fwd");
-}
-extern "C" int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int cols, float scale, int dtype,
+// P may alias S and dS may alias dP only when dtype is fp32.  ld = row stride (elements) of every matrix, >= cols:
+// rows padded to a multiple of 8 elements keep bf16 P / dS usable as TMA operands of the tensor-core GEMMs.
+extern "C" int sidlsg_softmax_fwd(const float* S, void* P, long rows, int cols, long ld, float scale, int dtype,
                                   void* stream) {
   if (rows == 0 || cols == 0) return SIDLSG_OK;
+  if (ld < cols) { set_error("softmax_fwd: ld < cols"); return SIDLSG_ERR_ARG; }
   int wpr = cols <= 256;
   long blocks = wpr ? (rows + 7) / 8 : rows;
-  SID_DISPATCH_DTYPE(dtype, T, (softmax_bwd_kernel<float, T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)P, dP, (T*)dS, rows, cols, scale, wpr)));
+  SID_DISPATCH_DTYPE(dtype, T, (softmax_fwd_kernel<float, T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, (T*)P, rows, cols, ld, scale, wpr)));
+  return check_launch("softmax_fwd");
+}
+extern "C" int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int cols, long ld, float scale,
+                                  int dtype, void* stream) {
+  if (rows == 0 || cols == 0) return SIDLSG_OK;
+  if (ld < cols) { set_error("softmax_bwd: ld < cols"); return SIDLSG_ERR_ARG; }
+  int wpr = cols <= 256;
+  long blocks = wpr ? (rows + 7) / 8 : rows;
+  SID_DISPATCH_DTYPE(dtype, T, (softmax_bwd_kernel<float, T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)P, dP, (T*)dS, rows, cols, ld, scale, wpr)));
   return check_launch("softmax_bwd");
 }

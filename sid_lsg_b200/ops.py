@@ -232,7 +232,7 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 # --------------------------------------------------------------------------------------------------------------
 def _attn_chunk(B, heads, N, M):
-    per = heads * N * M * 4
+    per = heads * N * ((M + 7) // 8 * 8) * 4
     return max(1, min(B, _ATTN_SCORE_BYTES // max(per, 1)))
 
 
@@ -242,12 +242,15 @@ class AttentionFn(Function):
 
     @staticmethod
     def _scores(q, k, b0, cb, heads, N, M, C, d, scale):
-        S = torch.empty((cb, heads, N, M), dtype=torch.float32, device=q.device)
-        gemm(q[b0:], C, 1, k[b0:], C, 1, S, M, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=(heads * N * M, N * M),
+        """P = softmax(scale Q K^T) for batch rows [b0, b0+cb): [cb, heads, N, Mp] with rows padded to Mp = ceil8(M)
+        elements so the bf16 matrices are valid TMA operands of the batched tensor-core GEMMs (77 text keys -> 80)."""
+        Mp = (M + 7) // 8 * 8
+        S = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
+        gemm(q[b0:], C, 1, k[b0:], C, 1, S, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=(heads * N * Mp, N * Mp),
              nb=(cb, heads), in_dtype=dt(q), out_dtype=F32)
         P = S if q.dtype == torch.float32 else torch.empty(S.shape, dtype=q.dtype, device=q.device)
-        lib.call("softmax_fwd", ptr(S), ptr(P), cb * heads * N, M, scale, dt(P), stream())
-        return P
+        lib.call("softmax_fwd", ptr(S), ptr(P), cb * heads * N, M, Mp, scale, dt(P), stream())
+        return P, Mp
 
     @staticmethod
     def forward(ctx, q, k, v, heads):
@@ -273,8 +276,8 @@ class AttentionFn(Function):
         ctx.flash_bwd = False
         for b0 in range(0, B, cbs):
             cb = min(cbs, B - b0)
-            P = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
-            gemm(P, M, 1, v[b0:], 1, C, o[b0:], C, N, d, M, a_sb=(heads * N * M, N * M), b_sb=(M * C, d),
+            P, Mp = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
+            gemm(P, Mp, 1, v[b0:], 1, C, o[b0:], C, N, d, M, a_sb=(heads * N * Mp, N * Mp), b_sb=(M * C, d),
                  c_sb=(N * C, d), nb=(cb, heads))
             del P
         ctx.save_for_backward(q, k, v)
@@ -299,19 +302,19 @@ class AttentionFn(Function):
         dv = torch.empty_like(v)
         for b0 in range(0, B, cbs):
             cb = min(cbs, B - b0)
-            pb = (heads * N * M, N * M)
-            P = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
+            P, Mp = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
+            pb = (heads * N * Mp, N * Mp)
             # dV[j, c] = sum_i P[i, j] dO[i, c]
-            gemm(P, 1, M, do[b0:], 1, C, dv[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
+            gemm(P, 1, Mp, do[b0:], 1, C, dv[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
             # dP[i, j] = sum_c dO[i, c] V[j, c]
-            dP = torch.empty((cb, heads, N, M), dtype=torch.float32, device=q.device)
-            gemm(do[b0:], C, 1, v[b0:], C, 1, dP, M, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=pb, nb=(cb, heads),
+            dP = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
+            gemm(do[b0:], C, 1, v[b0:], C, 1, dP, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=pb, nb=(cb, heads),
                  in_dtype=dt(q), out_dtype=F32)
             dS = dP if q.dtype == torch.float32 else torch.empty(dP.shape, dtype=q.dtype, device=q.device)
-            lib.call("softmax_bwd", ptr(P), ptr(dP), ptr(dS), cb * heads * N, M, scale, dt(dS), stream())
+            lib.call("softmax_bwd", ptr(P), ptr(dP), ptr(dS), cb * heads * N, M, Mp, scale, dt(dS), stream())
             # dQ[i, c] = sum_j dS[i, j] K[j, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]
-            gemm(dS, M, 1, k[b0:], 1, C, dq[b0:], C, N, d, M, a_sb=pb, b_sb=(M * C, d), c_sb=(N * C, d), nb=(cb, heads))
-            gemm(dS, 1, M, q[b0:], 1, C, dk[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
+            gemm(dS, Mp, 1, k[b0:], 1, C, dq[b0:], C, N, d, M, a_sb=pb, b_sb=(M * C, d), c_sb=(N * C, d), nb=(cb, heads))
+            gemm(dS, 1, Mp, q[b0:], 1, C, dk[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
             del P, dP, dS
         return dq, dk, dv, None
 

@@ -35,7 +35,8 @@ def P(t, channels_last=False):
     return p
 
 
-@pytest.mark.parametrize("M,K,N", [(77, 48, 64), (512, 320, 640), (3, 1280, 320), (1024, 64, 136)])
+@pytest.mark.parametrize("M,K,N", [(77, 48, 64), (512, 320, 640), (3, 1280, 320), (1024, 64, 136), (32, 1280, 1280),
+                                   (16, 1280, 640), (100, 1280, 320), (32, 320, 1280)])
 def test_linear_fwd_bwd(M, K, N):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(M, K, generator=g)

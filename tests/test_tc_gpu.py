@@ -116,7 +116,8 @@ def test_tc_wgrad_accumulates():
 
 @pytest.mark.parametrize("B,N,M,C,heads", [(2, 4096, 4096, 320, 8), (2, 1024, 1024, 640, 8), (3, 256, 256, 1280, 8),
                                            (2, 64, 64, 1280, 8), (2, 4096, 77, 320, 8), (1, 1024, 1024, 640, 10),
-                                           (2, 256, 77, 1280, 20), (1, 200, 333, 128, 2)])
+                                           (2, 256, 77, 1280, 20), (1, 200, 333, 128, 2), (2, 256, 77, 1280, 8),
+                                           (3, 64, 77, 1280, 8)])
 def test_tc_flash_attention(B, N, M, C, heads):
     """tcgen05 flash attention vs fp32 softmax(QK^T/sqrt(d))V on bf16-rounded inputs (bf16 P and bf16 output:
     tolerance 2e-2 of the output scale); backward = tcgen05 flash backward for d <= 80, recompute path for d = 160."""
@@ -142,3 +143,45 @@ def test_tc_flash_attention(B, N, M, C, heads):
         check(qd.grad, qr.grad, 3e-2, "dq")
         check(kd.grad, kr.grad, 3e-2, "dk")
         check(vd.grad, vr.grad, 3e-2, "dv")
+
+
+@pytest.mark.parametrize("nb1,nb2,M,N,K,a_mn,b_mn,f32out", [(3, 8, 256, 256, 160, 0, 0, 1), (2, 8, 256, 77, 160, 0, 0, 1),
+                                                          (2, 4, 77, 160, 256, 1, 1, 0), (2, 4, 256, 160, 77, 0, 1, 0),
+                                                          (1, 5, 64, 160, 64, 1, 1, 0), (2, 3, 300, 96, 200, 0, 0, 0)])
+def test_tc_batched_gemm(nb1, nb2, M, N, K, a_mn, b_mn, f32out):
+    """nb1 x nb2 independent GEMMs in ONE tcgen05 launch (4-D operand maps): the score / value contractions of the
+    d = 160 attention backward, incl. 77 text keys on rows padded to 80 elements.  Must not fall back to CUDA cores."""
+    from sid_lsg_b200._lib import lib, F32
+    import ctypes
+    o = ops()
+    g = torch.Generator().manual_seed(7)
+    Kp, Mp, Np = (K + 7) // 8 * 8, (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    # physical layouts with padded leading dimensions; pad columns hold NaN to prove they are never read
+    if a_mn:
+        A = torch.full((nb1, nb2, K, Mp), float("nan")); A[..., :M] = bf(torch.randn(nb1, nb2, K, M, generator=g))
+        a_log = A[..., :M].transpose(-1, -2)
+        a_sm, a_sk, a_sb = 1, Mp, (nb2 * K * Mp, K * Mp)
+    else:
+        A = torch.full((nb1, nb2, M, Kp), float("nan")); A[..., :K] = bf(torch.randn(nb1, nb2, M, K, generator=g))
+        a_log = A[..., :K]
+        a_sm, a_sk, a_sb = Kp, 1, (nb2 * M * Kp, M * Kp)
+    if b_mn:
+        Bm = torch.full((nb1, nb2, K, Np), float("nan")); Bm[..., :N] = bf(torch.randn(nb1, nb2, K, N, generator=g))
+        b_log = Bm[..., :N]
+        b_sn, b_sk, b_sb = 1, Np, (nb2 * K * Np, K * Np)
+    else:
+        Bm = torch.full((nb1, nb2, N, Kp), float("nan")); Bm[..., :K] = bf(torch.randn(nb1, nb2, N, K, generator=g))
+        b_log = Bm[..., :K].transpose(-1, -2)
+        b_sn, b_sk, b_sb = Kp, 1, (nb2 * N * Kp, N * Kp)
+    ref = a_log.float() @ b_log.float()
+    ldc = Np
+    C = torch.zeros((nb1, nb2, M, ldc), dtype=torch.float32 if f32out else torch.bfloat16, device=DEV)
+    cnt = (ctypes.c_long * 2)()
+    lib.query("counters", cnt)
+    simt0 = cnt[1]
+    o.gemm(A.to(DEV).bfloat16(), a_sm, a_sk, Bm.to(DEV).bfloat16(), b_sn, b_sk, C, ldc, M, N, K, a_sb=a_sb, b_sb=b_sb,
+           c_sb=(nb2 * M * ldc, M * ldc), nb=(nb1, nb2), out_dtype=F32 if f32out else None)
+    torch.cuda.synchronize()
+    lib.query("counters", cnt)
+    assert cnt[1] == simt0, "batched GEMM fell back to the CUDA-core kernel"
+    check(C[..., :N], ref, 2e-3 if f32out else 1.5e-2, "C")
