@@ -98,19 +98,22 @@ int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int 
                        void* stream);
 
 /* Flash attention on tcgen05/TMEM/TMA (bf16): o = softmax(q k^T / sqrt(d)) v per (batch, head) with no score
- * matrix in HBM.  q [B,N,H*d], k/v [B,M,H*d], o [B,N,H*d] bf16 contiguous, heads interleaved in the channel dim;
+ * matrix in HBM.  q [B,N,H*d], k/v [B,M,H*d] bf16 with row strides ldq/ldk/ldv elements (H*d when dense, 3*H*d for
+ * the thirds of a packed q|k|v projection; batch stride = rows * ld), o [B,N,H*d] dense, heads interleaved in the channel dim;
  * lse [B,H,N] fp32 = log-sum-exp of the scaled scores (kept for the backward; may be null).  d % 8 == 0,
  * 16 <= d <= 192.  Returns SIDLSG_ERR_UNSUPPORTED if the device / shape cannot take the tensor-core path.
  * ref: the attention call of every BasicTransformerBlock.attn1/attn2 (xformers / SDPA in the reference). */
 int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
-                         int M, int H, int d, void* stream);
+                         int M, int H, int d, long ldq, long ldk, long ldv, void* stream);
 
 /* Backward of the above with the scores recomputed on the tensor cores: dq [B,N,H*d], dk/dv [B,M,H*d] bf16.
  * delta: fp32 [B,H,N] scratch (= sum_c o*dout, computed here); dq_acc: fp32 [B,N,H*d] scratch (zeroed here; dQ
- * partials of the K/V tiles are reduced into it with red.global.add).  d % 8 == 0, 16 <= d <= 80. */
+ * partials of the K/V tiles are reduced into it with red.global.add).  d % 8 == 0, 16 <= d <= 80.
+ * ld*: row strides (elements) of q/k/v and of the dq/dk/dv outputs (slices of packed tensors allowed). */
 int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                          const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
-                         int B, int N, int M, int H, int d, void* stream);
+                         int B, int N, int M, int H, int d, long ldq, long ldk, long ldv, long lddq, long lddk,
+                         long lddv, void* stream);
 
 /* ---- elementwise ----------------------------------------------------------------------------------------- */
 /* UNet boundary: fp32 NCHW [B,C,HW] <-> token-major [B,HW,C] in the compute dtype (sample in, .sample out). */

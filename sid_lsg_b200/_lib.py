@@ -109,7 +109,7 @@ class KernelTimer:
             return ("flop", 4.0 * a[5] * a[6] * a[7] * a[8] * a[9])
 
         def attn_bwd(a):  # 5 contractions (S recompute, dP, dV, dK, dQ)
-            return ("flop", 10.0 * a[-6] * a[-5] * a[-4] * a[-3] * a[-2])
+            return ("flop", 10.0 * a[11] * a[12] * a[13] * a[14] * a[15])
 
         def gn_fwd(a):    # B, HW, C at 9..11; read x twice (stats + apply), write y
             return ("byte", 3.0 * a[9] * a[10] * a[11] * (4 if a[15] == 0 else 2))
@@ -142,7 +142,7 @@ class KernelTimer:
         if name == "attention_fwd":
             return "B%d N%d M%d H%d d%d" % tuple(a[5:10])
         if name == "attention_bwd":
-            return "B%d N%d M%d H%d d%d" % tuple(a[-6:-1])
+            return "B%d N%d M%d H%d d%d" % tuple(a[11:16])
         if name in ("groupnorm_fwd", "groupnorm_bwd"):
             return "B%d HW%d C%d" % ((a[9], a[10], a[11]) if name == "groupnorm_fwd" else (a[13], a[14], a[15]))
         return ""

@@ -347,10 +347,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int len, int B) {
-  const long C = (long)H * d;
+// head-sliced view of a [B, len, >= H*d] bf16 tensor with row stride ld elements (ld = H*d when dense; 3*H*d for
+// the q/k/v thirds of a packed projection output): dims (d, H, len, B)
+static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int len, int B, long ld) {
   uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)len, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)C * 2, (uint64_t)len * C * 2};
+  uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)len * ld * 2};
   uint32_t box[4] = {64, 1, 128, 1};
   return make_map(m, base, 4, dims, strides, box);
 }
@@ -361,14 +362,19 @@ static bool g_attn_attr_done = false;
 
 using namespace sidlsg;
 
-// q [B,N,H*d], k/v [B,M,H*d] bf16 contiguous; o [B,N,H*d] bf16; lse [B,H,N] fp32 (natural log, may be null).
+// q [B,N,H*d], k/v [B,M,H*d] bf16 with row strides ldq/ldk/ldv elements (batch stride = rows * ld; multiples of 8);
+// o [B,N,H*d] bf16 dense; lse [B,H,N] fp32 (natural log, may be null).
 // Returns SIDLSG_ERR_UNSUPPORTED when the tensor-core path cannot take the shape (caller uses the fp32-exact path).
 extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
-                                    int M, int H, int d, void* stream) {
+                                    int M, int H, int d, long ldq, long ldk, long ldv, void* stream) {
   if (!tc_enabled()) { set_error("attention_fwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
   if (d % 8 || d < 16 || d > 192 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
     set_error("attention_fwd: unsupported shape B=%d N=%d M=%d H=%d d=%d", B, N, M, H, d);
     return SIDLSG_ERR_UNSUPPORTED;
+  }
+  if (ldq < (long)H * d || ldk < (long)H * d || ldv < (long)H * d || ((ldq | ldk | ldv) & 7)) {
+    set_error("attention_fwd: row strides must be >= H*d and multiples of 8 elements");
+    return SIDLSG_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
   AttnParams p;
@@ -381,7 +387,8 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = (bf16*)o; p.lse = lse;
   CUtensorMap tq, tk, tv;
-  if (!make_head_map(&tq, q, d, H, N, B) || !make_head_map(&tk, k, d, H, M, B) || !make_head_map(&tv, v, d, H, M, B))
+  if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
+      !make_head_map(&tv, v, d, H, M, B, ldv))
     return SIDLSG_ERR_CUDA;
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
   if (!g_attn_attr_done) {
@@ -422,6 +429,7 @@ struct AttnBwdParams {
   int stage_alias;       // dQ staging aliases the P^T/dS^T tiles (d > 64)
   bf16* dk;
   bf16* dv;
+  long lddk, lddv;       // row strides (elements) of dk / dv
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -697,7 +705,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // the last dq_full commit covered every MMA: dV / dK accumulators are final. wg0 stores dV, wg1 stores dK.
     {
       const uint32_t acc = wg == 0 ? dv_tmem : dk_tmem;
-      bf16* out = (wg == 0 ? p.dv : p.dk) + ((long)b * p.M + kv0 + row) * C + h * p.d;
+      bf16* out = (wg == 0 ? p.dv : p.dk) + ((long)b * p.M + kv0 + row) * (wg == 0 ? p.lddv : p.lddk) + h * p.d;
       for (int cc = 0; cc < p.dpad; cc += 16) {
         uint32_t r[16];
         tmem_ld16_nowait(acc + lane_off + cc, r);
@@ -750,22 +758,44 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
   }
 }
 
+// dq (bf16, row stride ld) = dq_acc (fp32 dense [rows, C]); 8 elements per thread
+__global__ void attn_dq_cast_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long rows, int C, long ld) {
+  const int vpr = C >> 3;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * vpr) return;
+  const long r = i / vpr;
+  const int c = (int)(i - r * vpr) << 3;
+  const float4 a = *reinterpret_cast<const float4*>(acc + r * C + c);
+  const float4 b2 = *reinterpret_cast<const float4*>(acc + r * C + c + 4);
+  uint4 o;
+  o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b2.x, b2.y); o.w = pack_bf16(b2.z, b2.w);
+  *reinterpret_cast<uint4*>(dq + r * ld + c) = o;
+}
+
 static bool g_attn_bwd_attr_done = false;
 
 }  // namespace sidlsg
 
-extern "C" int sidlsg_cast(const void* x, void* y, long n, int in_dtype, int out_dtype, void* stream);
-
 // dq_acc: fp32 [B,N,H*d] scratch (zeroed here), delta: fp32 [B,H,N] scratch.  dq/dk/dv bf16 outputs.
+// q/k/v and dq/dk/dv may be column slices of packed tensors: ld* = their row strides in elements (o, dout dense).
 // Supports d % 8 == 0, 16 <= d <= 80 (TMEM: 256 + 3*dpad <= 512 columns); returns SIDLSG_ERR_UNSUPPORTED otherwise.
 extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                                     const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
-                                    int B, int N, int M, int H, int d, void* stream) {
+                                    int B, int N, int M, int H, int d, long ldq, long ldk, long ldv, long lddq,
+                                    long lddk, long lddv, void* stream) {
   if (!tc_enabled()) { set_error("attention_bwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
   const int dpad = (d + 15) & ~15;
   if (d % 8 || d < 16 || 256 + 3 * dpad > 512 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
     set_error("attention_bwd: unsupported shape B=%d N=%d M=%d H=%d d=%d", B, N, M, H, d);
     return SIDLSG_ERR_UNSUPPORTED;
+  }
+  {
+    const long C0 = (long)H * d;
+    if (ldq < C0 || ldk < C0 || ldv < C0 || lddq < C0 || lddk < C0 || lddv < C0 ||
+        ((ldq | ldk | ldv | lddq | lddk | lddv) & 7)) {
+      set_error("attention_bwd: row strides must be >= H*d and multiples of 8 elements");
+      return SIDLSG_ERR_ARG;
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long nq = (long)B * N * H;
@@ -780,10 +810,11 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   p.scale = 1.f / sqrtf((float)d);
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+  p.lddk = lddk; p.lddv = lddv;
   p.stage_alias = d > 64;
   CUtensorMap tq, tk, tv, tdo, tdq;
-  if (!make_head_map(&tq, q, d, H, N, B) || !make_head_map(&tk, k, d, H, M, B) || !make_head_map(&tv, v, d, H, M, B) ||
-      !make_head_map(&tdo, dout, d, H, N, B))
+  if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
+      !make_head_map(&tv, v, d, H, M, B, ldv) || !make_head_map(&tdo, dout, d, H, N, B, (long)H * d))
     return SIDLSG_ERR_CUDA;
   {
     const long C = (long)H * d;
@@ -803,5 +834,10 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;
   // dq (bf16) = dq_acc (fp32)
-  return sidlsg_cast(dq_acc, dq, (long)B * N * H * d, SIDLSG_F32, SIDLSG_BF16, stream);
+  {
+    const long rows = (long)B * N;
+    const int C = H * d;
+    attn_dq_cast_kernel<<<(unsigned)((rows * (C >> 3) + 255) / 256), 256, 0, st>>>(dq_acc, (bf16*)dq, rows, C, lddq);
+  }
+  return check_launch("attention_bwd dq cast");
 }

@@ -241,41 +241,62 @@ static int pick_ksplit(int M, int N, int K, int nbatch) {
 // weight-bandwidth bound: the weight matrix is streamed exactly once with coalesced / 128-bit accesses.
 constexpr int SK_M = 32;
 
-// C[m][n] = sum_k A[m][k] W[n][k]   (W K-contiguous): one warp per output column n, lanes split K
+// C[m][n] = sum_k A[m][k] W[n][k]   (W K-contiguous): one warp per SK_NW output columns, lanes split K in float4s, so
+// every A quad fetched (L1-resident, shared by all warps) feeds 4 * SK_NW FMAs; blockIdx.y = K slab (slabs meet
+// through fp32 atomics when gridDim.y > 1: the caller zeroes C first unless it accumulates).
+constexpr int SK_NW = 4;
 __global__ void __launch_bounds__(256)
 skinny_nt_kernel(const float* __restrict__ A, long a_sm, const float* __restrict__ W, long w_sn, float* __restrict__ C,
                  long ldc, const float* __restrict__ bias, const float* __restrict__ res, long ldr, int M, int N, int K,
-                 float alpha, int accumulate) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+                 int kslab, float alpha, int accumulate) {
+  const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SK_NW;
   const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  float acc[SK_M];
+  if (n0 >= N) return;
+  const int k0 = blockIdx.y * kslab, k1 = min(K, k0 + kslab);
+  float acc[SK_M][SK_NW];
 #pragma unroll
-  for (int m = 0; m < SK_M; ++m) acc[m] = 0.f;
-  const float* w = W + (long)n * w_sn;
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 wv = (k + 3 < K) ? *reinterpret_cast<const float4*>(w + k)
-                            : make_float4(w[k], k + 1 < K ? w[k + 1] : 0.f, k + 2 < K ? w[k + 2] : 0.f, 0.f);
+  for (int m = 0; m < SK_M; ++m)
+#pragma unroll
+    for (int j = 0; j < SK_NW; ++j) acc[m][j] = 0.f;
+  for (int k = k0 + lane * 4; k < k1; k += 128) {
+    const bool full = k + 3 < k1;
+    float4 wv[SK_NW];
+#pragma unroll
+    for (int j = 0; j < SK_NW; ++j) {
+      const float* w = W + (long)min(n0 + j, N - 1) * w_sn + k;
+      wv[j] = full ? *reinterpret_cast<const float4*>(w)
+                   : make_float4(w[0], k + 1 < k1 ? w[1] : 0.f, k + 2 < k1 ? w[2] : 0.f, 0.f);
+    }
 #pragma unroll
     for (int m = 0; m < SK_M; ++m) {
       if (m < M) {
         const float* a = A + (long)m * a_sm + k;
-        float4 av = (k + 3 < K) ? *reinterpret_cast<const float4*>(a)
-                                : make_float4(a[0], k + 1 < K ? a[1] : 0.f, k + 2 < K ? a[2] : 0.f, 0.f);
-        acc[m] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[m]))));
+        const float4 av = full ? *reinterpret_cast<const float4*>(a)
+                               : make_float4(a[0], k + 1 < k1 ? a[1] : 0.f, k + 2 < k1 ? a[2] : 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < SK_NW; ++j)
+          acc[m][j] = fmaf(av.x, wv[j].x, fmaf(av.y, wv[j].y, fmaf(av.z, wv[j].z, fmaf(av.w, wv[j].w, acc[m][j]))));
       }
     }
   }
+  const bool first = blockIdx.y == 0;
 #pragma unroll
   for (int m = 0; m < SK_M; ++m) {
     if (m < M) {
-      float v = warp_sum(acc[m]);
-      if (lane == 0) {
-        v *= alpha;
-        if (bias) v += bias[n];
-        if (res) v += res[(long)m * ldr + n];
-        float* dst = C + (long)m * ldc + n;
-        *dst = accumulate ? *dst + v : v;
+#pragma unroll
+      for (int j = 0; j < SK_NW; ++j) {
+        float v = warp_sum(acc[m][j]);
+        const int n = n0 + j;
+        if (lane == 0 && n < N) {
+          v *= alpha;
+          if (first) {
+            if (bias) v += bias[n];
+            if (res) v += res[(long)m * ldr + n];
+          }
+          float* dst = C + (long)m * ldc + n;
+          if (gridDim.y > 1) atomicAdd(dst, v);
+          else *dst = accumulate ? *dst + v : v;
+        }
       }
     }
   }
@@ -339,10 +360,17 @@ static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long
   if (rowvec) return 0;
   if (M <= 4 * SK_M && a_sk == 1 && b_sk == 1 && (a_sm % 4) == 0 && (b_sn % 4) == 0 &&
       ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    const int nblk = cdiv(N, 8 * SK_NW);
+    int ks = (148 + nblk - 1) / nblk;                 // enough K slabs to cover the SMs ...
+    if (ks > K / 256) ks = K / 256;                   // ... of at least 256 reduction elements each
+    if (ks < 1) ks = 1;
+    const int kslab = (cdiv(K, ks) + 3) / 4 * 4;
+    ks = cdiv(K, kslab);
+    if (ks > 1 && !accumulate) cudaMemset2DAsync(c, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
     for (int m0 = 0; m0 < M; m0 += SK_M)
-      skinny_nt_kernel<<<cdiv(N, 8), 256, 0, st>>>(a + m0 * a_sm, a_sm, b, b_sn, c + m0 * ldc, ldc, bias,
-                                                    res ? res + m0 * ldr : nullptr, ldr, min(SK_M, M - m0), N, K, alpha,
-                                                    accumulate);
+      skinny_nt_kernel<<<dim3(nblk, ks), 256, 0, st>>>(a + m0 * a_sm, a_sm, b, b_sn, c + m0 * ldc, ldc, bias,
+                                                        res ? res + m0 * ldr : nullptr, ldr, min(SK_M, M - m0), N, K,
+                                                        kslab, alpha, accumulate);
     return check_launch("skinny_nt") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
   }
   if (M <= 4 * SK_M && b_sn == 1 && !bias && !res) {

@@ -252,8 +252,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase[2] = {0, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
-      mbar_wait(tfull_bar(acc), acc_phase[acc]);
-      tc_fence_after();
       const int m = t.m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const bool has_work = t.kb1 > t.kb0;
@@ -268,8 +266,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         (!p.res || (((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
                         (!p.rowvec || (((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0)));
+      // bf16 residual of this thread's columns, fetched BEFORE the accumulator is complete: the DRAM latency of the
+      // residual tile hides behind the main loop instead of serialising the epilogue (K = 320 GEMMs are output-bound)
+      uint4 rpre[16];
+      const bool pre = fast && p.res && !p.out_f32 && row_ok && has_work;
+      if (pre) {
+        const bf16* rp0 = reinterpret_cast<const bf16*>(p.res) + (long)m * p.ldr + t.col0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = grp * 32 + ci * 64;
+          if (c < t.n_valid) {
+            rpre[4 * ci] = *reinterpret_cast<const uint4*>(rp0 + c);
+            rpre[4 * ci + 1] = *reinterpret_cast<const uint4*>(rp0 + c + 8);
+            if (c + 32 <= t.n_valid) {
+              rpre[4 * ci + 2] = *reinterpret_cast<const uint4*>(rp0 + c + 16);
+              rpre[4 * ci + 3] = *reinterpret_cast<const uint4*>(rp0 + c + 24);
+            }
+          }
+        }
+      }
+      mbar_wait(tfull_bar(acc), acc_phase[acc]);
+      tc_fence_after();
       if (fast) {
-        for (int c = grp * 32; c < t.n_valid; c += 64) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = grp * 32 + ci * 64;
+          if (c >= t.n_valid) break;
           const bool two = c + 32 <= t.n_valid;     // 32 columns, or a 16-column tail
           uint32_t r[32];
           __syncwarp();
@@ -320,9 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               } else {
                 bf16* cp = reinterpret_cast<bf16*>(p.c) + crow + cc;
-                if (p.res) {
-                  const bf16* rp = reinterpret_cast<const bf16*>(p.res) + (long)m * p.ldr + t.col0 + cc;
-                  const uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
+                if (pre) {
+                  const uint4 r0 = rpre[4 * ci + 2 * hblk], r1 = rpre[4 * ci + 2 * hblk + 1];
                   const __nv_bfloat162* e0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
                   const __nv_bfloat162* e1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll

@@ -45,9 +45,9 @@ class LinearFn(Function):
     def forward(ctx, x, weight, wc, bias, res, owner):
         require_cuda(x, wc)
         x = _c(x)
-        N = weight.shape[0]
-        K = weight.numel() // N
-        assert x.shape[-1] == K, (x.shape, weight.shape)
+        N = wc.shape[0]                      # wc may be a FUSED weight: several [Ni, K] parameters stacked in the bucket
+        K = wc.numel() // N
+        assert x.shape[-1] == K, (x.shape, wc.shape)
         M = x.numel() // K
         y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
         if res is not None:
@@ -76,6 +76,39 @@ class LinearFn(Function):
 
 def linear(x, weight, bias=None, res=None):
     return LinearFn.apply(x, weight, compute_weight(weight, x.dtype), bias, res, (weight, bias))
+
+
+class FusedWeight:
+    """Several bias-free Linear weights [Ni, K] that sit back to back in the flat buckets (to_q|to_k|to_v, to_k|to_v)
+    viewed as ONE [sum Ni, K] matrix: `master` / `shadow` / `grad` are views of the network's buckets, so the fused
+    GEMM reads the same bytes the separate ones would and its weight gradient lands in the same gradient slots."""
+
+    def __init__(self, params):
+        first = params[0]
+        K = first.shape[1]
+        n = sum(p.shape[0] for p in params)
+        flat = first._flat
+        off = first.data.storage_offset()
+        expect = off
+        for p in params:
+            if p.dim() != 2 or p.shape[1] != K or p._flat is not flat or p.data.storage_offset() != expect or not p.data.is_contiguous():
+                raise ValueError("parameters are not contiguous in the flat bucket")
+            expect += p.numel()
+        self.first = first
+        self.flat = flat
+        self.shape = (n, K)
+        self.master = flat.master[off:off + n * K].view(n, K)
+        self.grad = flat.grad[off:off + n * K].view(n, K)
+        self._shadow = flat.shadow[off:off + n * K].view(n, K) if flat.shadow is not None else None
+
+    def compute(self, dtype):
+        return self.master if dtype == torch.float32 else self._shadow
+
+
+def linear_fused(x, fused):
+    """y = x [W1; W2; ...]^T for a FusedWeight (no bias).  `fused.first` is the autograd handle: the weights share
+    their requires_grad state, and the weight gradient is written by the wgrad kernel into fused.grad directly."""
+    return LinearFn.apply(x, fused.first, fused.compute(x.dtype), None, None, (fused, None))
 
 
 def compute_weight(p, dtype):
@@ -236,91 +269,151 @@ def _attn_chunk(B, heads, N, M):
     return max(1, min(B, _ATTN_SCORE_BYTES // max(per, 1)))
 
 
-class AttentionFn(Function):
-    """softmax(Q K^T / sqrt(d)) V per head; q [B,N,C], k/v [B,M,C], heads interleaved in C (head h = channels
-    [h d, (h+1) d)).  fp32-exact path: fp32 scores materialised per batch chunk, recomputed in backward."""
+def _rows(t):
+    """[B, L, C] view with unit channel stride and batch stride L * row stride (dense, or a column slice of a packed
+    projection output) -> row stride in elements."""
+    B, L, C = t.shape
+    ld = t.stride(1)
+    assert t.stride(2) == 1 and (B == 1 or t.stride(0) == L * ld), "attention operand must be a row-strided [B,L,C] view"
+    return ld
 
-    @staticmethod
-    def _scores(q, k, b0, cb, heads, N, M, C, d, scale):
-        """P = softmax(scale Q K^T) for batch rows [b0, b0+cb): [cb, heads, N, Mp] with rows padded to Mp = ceil8(M)
-        elements so the bf16 matrices are valid TMA operands of the batched tensor-core GEMMs (77 text keys -> 80)."""
-        Mp = (M + 7) // 8 * 8
-        S = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
-        gemm(q[b0:], C, 1, k[b0:], C, 1, S, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=(heads * N * Mp, N * Mp),
-             nb=(cb, heads), in_dtype=dt(q), out_dtype=F32)
-        P = S if q.dtype == torch.float32 else torch.empty(S.shape, dtype=q.dtype, device=q.device)
-        lib.call("softmax_fwd", ptr(S), ptr(P), cb * heads * N, M, Mp, scale, dt(P), stream())
-        return P, Mp
+
+def _scores(q, k, b0, cb, heads, N, M, d, scale):
+    """P = softmax(scale Q K^T) for batch rows [b0, b0+cb): [cb, heads, N, Mp] with rows padded to Mp = ceil8(M)
+    elements so the bf16 matrices are valid TMA operands of the batched tensor-core GEMMs (77 text keys -> 80)."""
+    Mp = (M + 7) // 8 * 8
+    lq, lk = _rows(q), _rows(k)
+    S = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
+    gemm(q[b0:], lq, 1, k[b0:], lk, 1, S, Mp, N, M, d, a_sb=(N * lq, d), b_sb=(M * lk, d), c_sb=(heads * N * Mp, N * Mp),
+         nb=(cb, heads), in_dtype=dt(q), out_dtype=F32)
+    P = S if q.dtype == torch.float32 else torch.empty(S.shape, dtype=q.dtype, device=q.device)
+    lib.call("softmax_fwd", ptr(S), ptr(P), cb * heads * N, M, Mp, scale, dt(P), stream())
+    return P, Mp
+
+
+def _attention_forward(q, k, v, heads, want_backward=True):
+    """softmax(Q K^T / sqrt(d)) V per head; q [B,N,C], k/v [B,M,C] row-strided views, heads interleaved in C (head h =
+    channels [h d, (h+1) d)).  Returns (o dense [B,N,C], saved-for-backward tuple, flash_bwd flag).
+    bf16: tcgen05 flash attention (scores never reach HBM); fp32-exact path: fp32 scores materialised per batch
+    chunk and recomputed in backward."""
+    require_cuda(q, k, v)
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    scale = float(d) ** -0.5
+    o = torch.empty((B, N, C), dtype=q.dtype, device=q.device)
+    if q.dtype == torch.bfloat16 and d % 8 == 0 and 16 <= d <= 192 and FLASH_ATTENTION:
+        lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+        lib.call("attention_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, N, M, heads, d, _rows(q), _rows(k), _rows(v),
+                 stream())
+        flash_bwd = d <= 80 and FLASH_ATTENTION_BWD
+        return o, ((o, lse) if (flash_bwd and want_backward) else ()), flash_bwd
+    cbs = _attn_chunk(B, heads, N, M)
+    lv = _rows(v)
+    for b0 in range(0, B, cbs):
+        cb = min(cbs, B - b0)
+        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale)
+        gemm(P, Mp, 1, v[b0:], 1, lv, o[b0:], C, N, d, M, a_sb=(heads * N * Mp, N * Mp), b_sb=(M * lv, d),
+             c_sb=(N * C, d), nb=(cb, heads))
+        del P
+    return o, (), False
+
+
+def _attention_backward(q, k, v, extra, flash_bwd, do, heads, dq, dk, dv):
+    """writes dq [B,N,C], dk/dv [B,M,C] (row-strided views, e.g. the thirds of one packed gradient tensor)."""
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    scale = float(d) ** -0.5
+    do = _c(do)
+    if flash_bwd:
+        o, lse = extra
+        delta = torch.empty_like(lse)
+        dq_acc = torch.empty((B, N, C), dtype=torch.float32, device=q.device)
+        lib.call("attention_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dq_acc),
+                 ptr(dq), ptr(dk), ptr(dv), B, N, M, heads, d, _rows(q), _rows(k), _rows(v), _rows(dq), _rows(dk),
+                 _rows(dv), stream())
+        return
+    cbs = _attn_chunk(B, heads, N, M)
+    lq, lk, lv, ldq, ldk, ldv = _rows(q), _rows(k), _rows(v), _rows(dq), _rows(dk), _rows(dv)
+    for b0 in range(0, B, cbs):
+        cb = min(cbs, B - b0)
+        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale)
+        pb = (heads * N * Mp, N * Mp)
+        # dV[j, c] = sum_i P[i, j] dO[i, c]
+        gemm(P, 1, Mp, do[b0:], 1, C, dv[b0:], ldv, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * ldv, d), nb=(cb, heads))
+        # dP[i, j] = sum_c dO[i, c] V[j, c]
+        dP = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
+        gemm(do[b0:], C, 1, v[b0:], lv, 1, dP, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * lv, d), c_sb=pb, nb=(cb, heads),
+             in_dtype=dt(q), out_dtype=F32)
+        dS = dP if q.dtype == torch.float32 else torch.empty(dP.shape, dtype=q.dtype, device=q.device)
+        lib.call("softmax_bwd", ptr(P), ptr(dP), ptr(dS), cb * heads * N, M, Mp, scale, dt(dS), stream())
+        # dQ[i, c] = sum_j dS[i, j] K[j, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]
+        gemm(dS, Mp, 1, k[b0:], 1, lk, dq[b0:], ldq, N, d, M, a_sb=pb, b_sb=(M * lk, d), c_sb=(N * ldq, d), nb=(cb, heads))
+        gemm(dS, 1, Mp, q[b0:], 1, lq, dk[b0:], ldk, M, d, N, a_sb=pb, b_sb=(N * lq, d), c_sb=(M * ldk, d), nb=(cb, heads))
+        del P, dP, dS
+
+
+class AttentionFn(Function):
+    """attention on separate dense q [B,N,C], k, v [B,M,C] tensors."""
 
     @staticmethod
     def forward(ctx, q, k, v, heads):
-        require_cuda(q, k, v)
         q, k, v = _c(q), _c(k), _c(v)
-        B, N, C = q.shape
-        M = k.shape[1]
-        d = C // heads
-        scale = float(d) ** -0.5
-        o = torch.empty_like(q)
-        cbs = _attn_chunk(B, heads, N, M)
-        if q.dtype == torch.bfloat16 and d % 8 == 0 and 16 <= d <= 192 and FLASH_ATTENTION:
-            # tensor-core flash attention (attention_tc.cu); scores never reach HBM
-            lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
-            lib.call("attention_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, N, M, heads, d, stream())
-            ctx.flash_bwd = d <= 80 and FLASH_ATTENTION_BWD
-            if ctx.flash_bwd:
-                ctx.save_for_backward(q, k, v, o, lse)
-            else:
-                ctx.save_for_backward(q, k, v)
-            ctx.cfg = (B, N, M, C, heads, d, scale, cbs)
-            return o
-        ctx.flash_bwd = False
-        for b0 in range(0, B, cbs):
-            cb = min(cbs, B - b0)
-            P, Mp = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
-            gemm(P, Mp, 1, v[b0:], 1, C, o[b0:], C, N, d, M, a_sb=(heads * N * Mp, N * Mp), b_sb=(M * C, d),
-                 c_sb=(N * C, d), nb=(cb, heads))
-            del P
-        ctx.save_for_backward(q, k, v)
-        ctx.cfg = (B, N, M, C, heads, d, scale, cbs)
+        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads)
+        ctx.save_for_backward(q, k, v, *extra)
+        ctx.heads = heads
         return o
 
     @staticmethod
     def backward(ctx, do):
-        B, N, M, C, heads, d, scale, cbs = ctx.cfg
-        do = _c(do)
-        if ctx.flash_bwd:
-            q, k, v, o, lse = ctx.saved_tensors
-            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-            delta = torch.empty_like(lse)
-            dq_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device)
-            lib.call("attention_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dq_acc),
-                     ptr(dq), ptr(dk), ptr(dv), B, N, M, heads, d, stream())
-            return dq, dk, dv, None
-        q, k, v = ctx.saved_tensors
-        dq = torch.empty_like(q)
-        dk = torch.empty_like(k)
-        dv = torch.empty_like(v)
-        for b0 in range(0, B, cbs):
-            cb = min(cbs, B - b0)
-            P, Mp = AttentionFn._scores(q, k, b0, cb, heads, N, M, C, d, scale)
-            pb = (heads * N * Mp, N * Mp)
-            # dV[j, c] = sum_i P[i, j] dO[i, c]
-            gemm(P, 1, Mp, do[b0:], 1, C, dv[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
-            # dP[i, j] = sum_c dO[i, c] V[j, c]
-            dP = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
-            gemm(do[b0:], C, 1, v[b0:], C, 1, dP, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * C, d), c_sb=pb, nb=(cb, heads),
-                 in_dtype=dt(q), out_dtype=F32)
-            dS = dP if q.dtype == torch.float32 else torch.empty(dP.shape, dtype=q.dtype, device=q.device)
-            lib.call("softmax_bwd", ptr(P), ptr(dP), ptr(dS), cb * heads * N, M, Mp, scale, dt(dS), stream())
-            # dQ[i, c] = sum_j dS[i, j] K[j, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]
-            gemm(dS, Mp, 1, k[b0:], 1, C, dq[b0:], C, N, d, M, a_sb=pb, b_sb=(M * C, d), c_sb=(N * C, d), nb=(cb, heads))
-            gemm(dS, 1, Mp, q[b0:], 1, C, dk[b0:], C, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * C, d), nb=(cb, heads))
-            del P, dP, dS
+        q, k, v, *extra = ctx.saved_tensors
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv)
         return dq, dk, dv, None
+
+
+class PackedAttentionFn(Function):
+    """attention on PACKED projections: a = [B,N,3C] (q|k|v thirds of one fused to_q/to_k/to_v GEMM; self-attention)
+    or a = q [B,N,C] with b = [B,M,2C] (k|v halves of one fused to_k/to_v GEMM; cross-attention).  The kernels read
+    the slices in place through row strides, and the backward writes dq|dk|dv straight into ONE packed gradient
+    tensor, so the projection's data gradient is a single GEMM over K = 3C (no per-branch gradients to add up)."""
+
+    @staticmethod
+    def _split(a, b):
+        if b is None:
+            C = a.shape[-1] // 3
+            return a[..., :C], a[..., C:2 * C], a[..., 2 * C:]
+        C = a.shape[-1]
+        return a, b[..., :C], b[..., C:]
+
+    @staticmethod
+    def forward(ctx, a, b, heads):
+        a = _c(a)
+        b = _c(b) if b is not None else None
+        q, k, v = PackedAttentionFn._split(a, b)
+        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads)
+        ctx.save_for_backward(a, b, *extra)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        a, b, *extra = ctx.saved_tensors
+        q, k, v = PackedAttentionFn._split(a, b)
+        da = torch.empty_like(a)
+        db = torch.empty_like(b) if b is not None else None
+        dq, dk, dv = PackedAttentionFn._split(da, db)
+        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv)
+        return da, db, None
 
 
 def attention(q, k, v, heads):
     return AttentionFn.apply(q, k, v, heads)
+
+
+def packed_attention(a, b, heads):
+    return PackedAttentionFn.apply(a, b, heads)
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,7 @@ class FlatParams:
                 p.data = view
                 p.grad = self._view_like(self.grad, p, o)
                 p._shadow = self._view_like(self.shadow, p, o) if shadow else None
+                p._flat = self
         if shadow:
             self.refresh_shadow()
 

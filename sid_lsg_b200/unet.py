@@ -126,8 +126,41 @@ class Attention(nn.Module):
         self.to_k = _Linear(kv, dim, bias=False)
         self.to_v = _Linear(kv, dim, bias=False)
         self.to_out = nn.ModuleList([_Linear(dim, dim), nn.Identity()])
+        self._fused_cache = {}
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_fused_cache"] = {}          # views of the flat buckets are rebuilt lazily, never pickled
+        return st
+
+    def _fused(self, names):
+        """FusedWeight over consecutive bias-free projections (built lazily per flat bucket; None when the module's
+        parameters are not flattened back to back, e.g. before flatten_())."""
+        ws = [getattr(self, n).weight for n in names]
+        flat = getattr(ws[0], "_flat", None)
+        key = (names, id(flat))
+        if self._fused_cache.get("key") != key:
+            fw = None
+            if flat is not None:
+                try:
+                    fw = ops.FusedWeight(ws)
+                except (ValueError, AttributeError):
+                    fw = None
+            self._fused_cache = {"key": key, "fw": fw}
+        return self._fused_cache["fw"]
 
     def forward(self, x, context, res):
+        if context is None:
+            fw = self._fused(("to_q", "to_k", "to_v"))
+            if fw is not None:
+                # one GEMM for q|k|v (x is read once), attention on the packed thirds
+                o = ops.packed_attention(ops.linear_fused(x, fw), None, self.heads)
+                return self.to_out[0](o, res=res)
+        else:
+            fw = self._fused(("to_k", "to_v"))
+            if fw is not None:
+                o = ops.packed_attention(self.to_q(x), ops.linear_fused(context, fw), self.heads)
+                return self.to_out[0](o, res=res)
         ctx = x if context is None else context
         q = self.to_q(x)
         k = self.to_k(ctx)
