@@ -18,8 +18,13 @@ full) for k in gemm_tc_kernel attn_fwd_kernel attn_bwd_kernel; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip ${SKIP:-40} -c 3 -f -o $OUT/$k \
           python bench.py --batch 16 --steps 1 --warmup 0 --no-cpu-baseline --no-roofline > $OUT/full_$k.log 2>&1
       done; ls -la $OUT;;
-prof) timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|attn_fwd|attn_bwd|gn_' -f -o $OUT/hot \
-        python scripts/prof_target.py > $OUT/prof.log 2>&1; tail -3 $OUT/prof.log
-      ncu -i $OUT/hot.ncu-rep --page raw --csv > $OUT/hot_raw.csv 2>/dev/null; ls -la $OUT;;
+prof) for sub in ${PROF:-attn gemm}; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gemm_tc|attn_fwd|attn_bwd|gn_' -f -o $OUT/hot_$sub \
+          python scripts/prof_target.py $sub > $OUT/prof_$sub.log 2>&1; tail -2 $OUT/prof_$sub.log
+        ncu -i $OUT/hot_$sub.ncu-rep --page raw --csv > $OUT/hot_${sub}_raw.csv 2>/dev/null
+        python scripts/ncu_lines.py $OUT/hot_$sub.ncu-rep 70 > $OUT/hot_${sub}_lines.txt 2>&1
+        sz=$(stat -c %s $OUT/hot_$sub.ncu-rep); echo "$sub report bytes $sz"
+        if [ "$sz" -gt 25000000 ]; then rm -f $OUT/hot_$sub.ncu-rep; echo "(report dropped: too large to bring back)"; fi
+      done; du -sh gpurun_out;;
 micro) timeout 600 python scripts/micro.py ${MICRO:-all} 5 > $OUT/micro.txt 2>&1; cat $OUT/micro.txt;;
 esac; done

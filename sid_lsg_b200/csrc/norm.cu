@@ -152,6 +152,42 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
   }
 }
 
+// y = [silu](x * a[b,c] + sh[b,c]) with the statistics kernels' geometry: a thread owns V consecutive channels (its
+// coefficients live in registers) and walks the rows of its chunk, so the loop body is one 16-byte load, V FMAs and
+// one 16-byte store; consecutive threads touch consecutive 16-byte pieces of the row-major tensor.
+template <class T, int V>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_rows_kernel(const T* __restrict__ x, const float* __restrict__ a, const float* __restrict__ sh,
+                     T* __restrict__ y, int HW, int C, int vpr, int iters, int rows_per_chunk, int silu) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y, VX = blockDim.x, RY = blockDim.y;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const long base = (long)b * HW * C;
+  for (int it = 0; it < iters; ++it) {
+    const int v = it * VX + tx;
+    if (v >= vpr) continue;
+    float av[V], sv[V];
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(a + (long)b * C + v * V + i);
+      const float4 s4 = *reinterpret_cast<const float4*>(sh + (long)b * C + v * V + i);
+      av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
+      sv[i] = s4.x; sv[i + 1] = s4.y; sv[i + 2] = s4.z; sv[i + 3] = s4.w;
+    }
+#pragma unroll 2
+    for (int r = r0 + ty; r < r1; r += RY) {
+      float e[V];
+      gn_load<T, V>(x + base + (long)r * C + v * V, e);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float t = fmaf(e[i], av[i], sv[i]);
+        e[i] = silu ? silu_f(t) : t;
+      }
+      gn_store<T, V>(y + base + (long)r * C + v * V, e);
+    }
+  }
+}
+
 // ---- backward ---------------------------------------------------------------------------------------------------
 // partial[b][chunk][c] = (sum dz, sum dz*xhat); dz = dy * silu'(x*a+sh) (or dy)
 template <class T, int V>
@@ -247,29 +283,44 @@ __global__ void gn_bwd_param_kernel(const float2* __restrict__ partial, float* _
   atomicAdd(dbeta + c, s);
 }
 
-template <class T, int VEC>
-__global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ a,
-                                    const float* __restrict__ sh, const float* __restrict__ P,
-                                    const float* __restrict__ Q, T* __restrict__ dx, long total_vec, int HWC, int C,
-                                    int silu) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_vec) return;
-  long e0 = i * VEC;
-  int b = (int)(e0 / HWC);
-  int c0 = (int)(e0 % C);
-  long o = (long)b * C + c0;
-  T xin[VEC], din[VEC], out[VEC];
-  *(uint4*)xin = *(const uint4*)(x + e0);
-  *(uint4*)din = *(const uint4*)(dy + e0);
+// dx = a * dz + x * P + Q, dz = dy * silu'(x*a+sh) (or dy); same row-walking geometry as gn_apply_rows_kernel
+template <class T, int V>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_rows_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ a,
+                         const float* __restrict__ sh, const float* __restrict__ P, const float* __restrict__ Q,
+                         T* __restrict__ dx, int HW, int C, int vpr, int iters, int rows_per_chunk, int silu) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y, VX = blockDim.x, RY = blockDim.y;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const long base = (long)b * HW * C;
+  for (int it = 0; it < iters; ++it) {
+    const int v = it * VX + tx;
+    if (v >= vpr) continue;
+    float av[V], sv[V], pv[V], qv[V];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    float xv = to_f(xin[j]);
-    float dz = to_f(din[j]);
-    float av = a[o + j];
-    if (silu) dz *= silu_grad_f(fmaf(xv, av, sh[o + j]));
-    out[j] = from_f<T>(fmaf(av, dz, fmaf(xv, P[o + j], Q[o + j])));
+    for (int i = 0; i < V; i += 4) {
+      const long o = (long)b * C + v * V + i;
+      const float4 a4 = *reinterpret_cast<const float4*>(a + o), s4 = *reinterpret_cast<const float4*>(sh + o);
+      const float4 p4 = *reinterpret_cast<const float4*>(P + o), q4 = *reinterpret_cast<const float4*>(Q + o);
+      av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
+      sv[i] = s4.x; sv[i + 1] = s4.y; sv[i + 2] = s4.z; sv[i + 3] = s4.w;
+      pv[i] = p4.x; pv[i + 1] = p4.y; pv[i + 2] = p4.z; pv[i + 3] = p4.w;
+      qv[i] = q4.x; qv[i + 1] = q4.y; qv[i + 2] = q4.z; qv[i + 3] = q4.w;
+    }
+#pragma unroll 2
+    for (int r = r0 + ty; r < r1; r += RY) {
+      float xe[V], de[V];
+      gn_load<T, V>(x + base + (long)r * C + v * V, xe);
+      gn_load<T, V>(dy + base + (long)r * C + v * V, de);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float dz = de[i];
+        if (silu) dz *= silu_grad_f(fmaf(xe[i], av[i], sv[i]));
+        de[i] = fmaf(av[i], dz, fmaf(xe[i], pv[i], qv[i]));
+      }
+      gn_store<T, V>(dx + base + (long)r * C + v * V, de);
+    }
   }
-  *(uint4*)(dx + e0) = *(uint4*)out;
 }
 
 // ---- LayerNorm ---------------------------------------------------------------------------------------
@@ -400,10 +451,11 @@ extern "C" int sidlsg_groupnorm_fwd(const void* x, const float* gamma, const flo
   else gn_launch_stats<bf16>((const bf16*)x, part, B, HW, C, st);
   gn_finalize_kernel<<<cdiv((long)B * G * 32, 256), 256, 0, st>>>(part, gamma, beta, mean, rstd, a, sh, B, C, G, HW, g.chunks, eps);
   long total = (long)B * HW * C;
+  const dim3 agrid(g.chunks, B), ablock(g.vx, g.ry);
   if (in_dtype == SIDLSG_F32 && out_dtype == SIDLSG_F32)
-    gn_apply_kernel<float, float, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)x, a, sh, (float*)y, total / 4, HW * C, C, silu);
+    gn_apply_rows_kernel<float, 4><<<agrid, ablock, 0, st>>>((const float*)x, a, sh, (float*)y, HW, C, C / 4, g.iters, g.rows_per_chunk, silu);
   else if (in_dtype == SIDLSG_BF16 && out_dtype == SIDLSG_BF16)
-    gn_apply_kernel<bf16, bf16, 8><<<cdiv(total / 8, 256), 256, 0, st>>>((const bf16*)x, a, sh, (bf16*)y, total / 8, HW * C, C, silu);
+    gn_apply_rows_kernel<bf16, 8><<<agrid, ablock, 0, st>>>((const bf16*)x, a, sh, (bf16*)y, HW, C, C / 8, g.iters, g.rows_per_chunk, silu);
   else if (in_dtype == SIDLSG_F32 && out_dtype == SIDLSG_BF16)
     gn_apply_kernel<float, bf16, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)x, a, sh, (bf16*)y, total / 4, HW * C, C, silu);
   else { set_error("groupnorm: unsupported dtype pair"); return SIDLSG_ERR_UNSUPPORTED; }
@@ -438,10 +490,11 @@ extern "C" int sidlsg_groupnorm_bwd(const void* dy, const void* x, const float* 
     const int ysplit = rows < 64 ? rows : 64;
     gn_bwd_param_kernel<<<dim3(cdiv(C, 128), ysplit), 128, 0, st>>>(part, dgamma, dbeta, rows, C);
   }
+  (void)total;
   if (dtype == SIDLSG_F32)
-    gn_bwd_apply_kernel<float, 4><<<cdiv(total / 4, 256), 256, 0, st>>>((const float*)dy, (const float*)x, a, sh, P, Q, (float*)dx, total / 4, HW * C, C, silu);
+    gn_bwd_apply_rows_kernel<float, 4><<<grid, block, 0, st>>>((const float*)dy, (const float*)x, a, sh, P, Q, (float*)dx, HW, C, C / 4, g.iters, g.rows_per_chunk, silu);
   else
-    gn_bwd_apply_kernel<bf16, 8><<<cdiv(total / 8, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, a, sh, P, Q, (bf16*)dx, total / 8, HW * C, C, silu);
+    gn_bwd_apply_rows_kernel<bf16, 8><<<grid, block, 0, st>>>((const bf16*)dy, (const bf16*)x, a, sh, P, Q, (bf16*)dx, HW, C, C / 8, g.iters, g.rows_per_chunk, silu);
   return check_launch("groupnorm_bwd");
 }
 
