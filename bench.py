@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list captures only)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     ap.add_argument("--shapes", default=None, help="write the per-shape kernel table of the roofline step to this file")
     return ap.parse_args()
@@ -271,8 +272,11 @@ def main():
         loss_host[2:].copy_(lg, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the loop reads the losses every iteration (:452, :535)
 
-    step_e2e(0)
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    if args.no_e2e:
+        ms_e2e = float("nan")
+    else:
+        step_e2e(0)
+        ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = args.batch * world / (ms_e2e / 1e3)
     h2d = nbytes(host[args.warmup][0]) + nbytes(host[args.warmup][1])
 

@@ -6,12 +6,12 @@ WHAT=${*:-tests bench list full}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 for w in $WHAT; do case $w in
-tests) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log; tail -5 $OUT/pytest.log;;
+tests) timeout 1200 python -m pytest tests -m gpu -q --maxfail=12 -p no:cacheprovider > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest.log | tail -20;;
 smoke) timeout 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
 bench) timeout 1500 python bench.py --shapes $OUT/shapes.txt > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json;;
 benchq) timeout 1500 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/shapes.txt > $OUT/bench.json 2> $OUT/bench.err; tail -c 1500 $OUT/bench.err; python scripts/bench_brief.py $OUT/bench.json;;
-list) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-roofline > $OUT/list_bench.log 2>&1
+list) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
+        python bench.py --batch 16 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-roofline > $OUT/list_bench.log 2>&1
       python scripts/ncu_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; rm -f $OUT/launches.csv.keep
       tail -30 $OUT/launches_summary.txt;;
 full) for k in gemm_tc_kernel attn_fwd_kernel attn_bwd_kernel; do

@@ -241,9 +241,13 @@ static int pick_ksplit(int M, int N, int K, int nbatch) {
 // weight-bandwidth bound: the weight matrix is streamed exactly once with coalesced / 128-bit accesses.
 constexpr int SK_M = 32;
 
-// C[m][n] = sum_k A[m][k] W[n][k]   (W K-contiguous): one warp per SK_NW output columns, lanes split K in float4s, so
-// every A quad fetched (L1-resident, shared by all warps) feeds 4 * SK_NW FMAs; blockIdx.y = K slab (slabs meet
-// through fp32 atomics when gridDim.y > 1: the caller zeroes C first unless it accumulates).
+// C[m][n] = sum_k A[m][k] W[n][k]   (W K-contiguous, K % 4 == 0): one warp per SK_NW output columns, lanes split K in
+// float4s, so every A quad fetched (L1-resident, shared by all warps) feeds 4 * SK_NW FMAs; blockIdx.y = K slab (slabs
+// meet through fp32 atomics when gridDim.y > 1: the caller zeroes C first unless it accumulates).
+// The cross-lane reduction is a butterfly that halves the live values at every step (31 shuffles per column instead
+// of 32 x 5) and leaves row m's total in lane m, so the whole kernel is ~1.5k instructions: the fully unrolled
+// predicated version it replaces was 38k instructions (600 KB of code) and spent ~100 us per launch missing the
+// instruction cache.
 constexpr int SK_NW = 4;
 __global__ void __launch_bounds__(256)
 skinny_nt_kernel(const float* __restrict__ A, long a_sm, const float* __restrict__ W, long w_sn, float* __restrict__ C,
@@ -253,51 +257,52 @@ skinny_nt_kernel(const float* __restrict__ A, long a_sm, const float* __restrict
   const int lane = threadIdx.x & 31;
   if (n0 >= N) return;
   const int k0 = blockIdx.y * kslab, k1 = min(K, k0 + kslab);
-  float acc[SK_M][SK_NW];
+  float acc[SK_NW][SK_M];
 #pragma unroll
-  for (int m = 0; m < SK_M; ++m)
+  for (int j = 0; j < SK_NW; ++j)
 #pragma unroll
-    for (int j = 0; j < SK_NW; ++j) acc[m][j] = 0.f;
+    for (int m = 0; m < SK_M; ++m) acc[j][m] = 0.f;
+  const float* wrow[SK_NW];
+#pragma unroll
+  for (int j = 0; j < SK_NW; ++j) wrow[j] = W + (long)min(n0 + j, N - 1) * w_sn;
   for (int k = k0 + lane * 4; k < k1; k += 128) {
-    const bool full = k + 3 < k1;
     float4 wv[SK_NW];
 #pragma unroll
-    for (int j = 0; j < SK_NW; ++j) {
-      const float* w = W + (long)min(n0 + j, N - 1) * w_sn + k;
-      wv[j] = full ? *reinterpret_cast<const float4*>(w)
-                   : make_float4(w[0], k + 1 < k1 ? w[1] : 0.f, k + 2 < k1 ? w[2] : 0.f, 0.f);
-    }
+    for (int j = 0; j < SK_NW; ++j) wv[j] = *reinterpret_cast<const float4*>(wrow[j] + k);
 #pragma unroll
     for (int m = 0; m < SK_M; ++m) {
-      if (m < M) {
-        const float* a = A + (long)m * a_sm + k;
-        const float4 av = full ? *reinterpret_cast<const float4*>(a)
-                               : make_float4(a[0], k + 1 < k1 ? a[1] : 0.f, k + 2 < k1 ? a[2] : 0.f, 0.f);
+      // rows >= M re-read row M-1 (their sums are never stored): no predicates in the unrolled body
+      const float4 av = *reinterpret_cast<const float4*>(A + (long)min(m, M - 1) * a_sm + k);
 #pragma unroll
-        for (int j = 0; j < SK_NW; ++j)
-          acc[m][j] = fmaf(av.x, wv[j].x, fmaf(av.y, wv[j].y, fmaf(av.z, wv[j].z, fmaf(av.w, wv[j].w, acc[m][j]))));
-      }
+      for (int j = 0; j < SK_NW; ++j)
+        acc[j][m] = fmaf(av.x, wv[j].x, fmaf(av.y, wv[j].y, fmaf(av.z, wv[j].z, fmaf(av.w, wv[j].w, acc[j][m]))));
     }
   }
   const bool first = blockIdx.y == 0;
+  const bool atomic = gridDim.y > 1;
 #pragma unroll
-  for (int m = 0; m < SK_M; ++m) {
-    if (m < M) {
+  for (int j = 0; j < SK_NW; ++j) {
 #pragma unroll
-      for (int j = 0; j < SK_NW; ++j) {
-        float v = warp_sum(acc[m][j]);
-        const int n = n0 + j;
-        if (lane == 0 && n < N) {
-          v *= alpha;
-          if (first) {
-            if (bias) v += bias[n];
-            if (res) v += res[(long)m * ldr + n];
-          }
-          float* dst = C + (long)m * ldc + n;
-          if (gridDim.y > 1) atomicAdd(dst, v);
-          else *dst = accumulate ? *dst + v : v;
-        }
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = up ? acc[j][i] : acc[j][i + off];
+        const float keep = up ? acc[j][i + off] : acc[j][i];
+        acc[j][i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
+    }
+    // acc[j][0] of lane m = sum over lanes of the original acc[j][m]
+    const int n = n0 + j;
+    if (lane < M && n < N) {
+      float v = acc[j][0] * alpha;
+      if (first) {
+        if (bias) v += bias[n];
+        if (res) v += res[(long)lane * ldr + n];
+      }
+      float* dst = C + (long)lane * ldc + n;
+      if (atomic) atomicAdd(dst, v);
+      else *dst = accumulate ? *dst + v : v;
     }
   }
 }
@@ -353,12 +358,25 @@ skinny_tn_kernel(const float* __restrict__ A, long a_sk, const float* __restrict
   *dst = accumulate ? *dst + alpha * acc : alpha * acc;
 }
 
+// C[0:M][0:N] = 0 for a row-strided fp32 matrix.  (cudaMemset2DAsync costs a DMA operation per row: ~4 us each,
+// 100-160 us for the 16-32 row outputs of the timestep projections - more than the GEMM it prepares.)
+__global__ void zero_rows_kernel(float* __restrict__ c, long ldc, int M, int N) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)M * N) return;
+  const long m = i / N;
+  c[m * ldc + (i - m * N)] = 0.f;
+}
+static void zero_rows(float* c, long ldc, int M, int N, cudaStream_t st) {
+  if (ldc == N) cudaMemsetAsync(c, 0, sizeof(float) * (size_t)M * N, st);
+  else zero_rows_kernel<<<cdiv((long)M * N, 256), 256, 0, st>>>(c, ldc, M, N);
+}
+
 // returns 1 if handled
 static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long b_sn, long b_sk, float* c, long ldc,
                       const float* bias, const float* res, long ldr, const float* rowvec, float alpha, int accumulate,
                       int M, int N, int K, cudaStream_t st) {
   if (rowvec) return 0;
-  if (M <= 4 * SK_M && a_sk == 1 && b_sk == 1 && (a_sm % 4) == 0 && (b_sn % 4) == 0 &&
+  if (M <= 4 * SK_M && a_sk == 1 && b_sk == 1 && (a_sm % 4) == 0 && (b_sn % 4) == 0 && (K % 4) == 0 &&
       ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
     const int nblk = cdiv(N, 8 * SK_NW);
     int ks = (148 + nblk - 1) / nblk;                 // enough K slabs to cover the SMs ...
@@ -366,7 +384,7 @@ static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long
     if (ks < 1) ks = 1;
     const int kslab = (cdiv(K, ks) + 3) / 4 * 4;
     ks = cdiv(K, kslab);
-    if (ks > 1 && !accumulate) cudaMemset2DAsync(c, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
+    if (ks > 1 && !accumulate) zero_rows(c, ldc, M, N, st);
     for (int m0 = 0; m0 < M; m0 += SK_M)
       skinny_nt_kernel<<<dim3(nblk, ks), 256, 0, st>>>(a + m0 * a_sm, a_sm, b, b_sn, c + m0 * ldc, ldc, bias,
                                                         res ? res + m0 * ldr : nullptr, ldr, min(SK_M, M - m0), N, K,
@@ -374,7 +392,7 @@ static int skinny_try(const float* a, long a_sm, long a_sk, const float* b, long
     return check_launch("skinny_nt") == SIDLSG_OK ? 1 : SIDLSG_ERR_CUDA;
   }
   if (M <= 4 * SK_M && b_sn == 1 && !bias && !res) {
-    if (!accumulate) cudaMemset2DAsync(c, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
+    if (!accumulate) zero_rows(c, ldc, M, N, st);
     for (int m0 = 0; m0 < M; m0 += SK_M)
       skinny_nn_kernel<<<dim3(cdiv(N, 128), cdiv(K, SK_KSLAB)), 128, 0, st>>>(
           a + m0 * a_sm, a_sm, a_sk, b, b_sk, c + m0 * ldc, ldc, min(SK_M, M - m0), N, K, alpha);

@@ -20,6 +20,10 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 namespace sidlsg {
 
@@ -32,7 +36,9 @@ constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;          // 32 KB (max block_n)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_OUT_BYTES = TC_BM * 64 * 2;         // 16 KB: one [128 rows][64 bf16] output chunk (SWIZZLE_128B)
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                              1024 /*bias*/;
 constexpr int TC_THREADS = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 
 struct TcParams {
@@ -59,6 +65,7 @@ struct TcParams {
   int rows_per_vec;
   float alpha;
   int atomic;               // fp32 red.add (split-K / gradient accumulation)
+  int tma_store;            // bf16 output leaves through smem staging + TMA bulk stores (tmC) instead of per-row stores
   // batched dense GEMMs (attention score / value contractions per (batch, head)): 4-D operand maps
   // (inner, outer, nb2, nb1); tile index = ((batch * m_tiles) + m) * n_tiles + n
   int batched, nb2;
@@ -110,16 +117,19 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-B alignment
-  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t out_base = smem_base + TC_STAGES * TC_STAGE_BYTES;   // 2 x 16 KB output staging (1024-B aligned)
+  const uint32_t bar_base = out_base + 2 * TC_OUT_BYTES;
   // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  const uint32_t bias_base = bar_base + 256;          // float[256]: bias of the current tile's columns (staged epilogue)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -129,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -250,6 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int grp = (warp - 4) >> 2;     // column-chunk parity this warp handles
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
+    uint32_t ochunk = 0;                 // output chunks staged so far (staging buffer = parity)
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
       const int m = t.m0 + q * 32 + lane;
@@ -285,9 +298,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      const bool ts = fast && p.tma_store;        // uniform over the 8 epilogue warps (depends on the tile only)
+      if (ts && p.bias) {
+        // bias of this tile's columns -> smem while the main loop is still running (the per-chunk __ldg's were the
+        // epilogue's largest stall).  Single buffer: every read of the previous tile's bias precedes that tile's last
+        // named barrier, every read of this one follows the first barrier below.
+        const int j = threadIdx.x - 128;
+        if (j < t.n_valid) bias_s[j] = __ldg(p.bias + t.col0 + j);
+      }
       mbar_wait(tfull_bar(acc), acc_phase[acc]);
       tc_fence_after();
-      if (fast) {
+      if (ts) {
+        // ---- staged epilogue: 64-column chunks -> bf16 SWIZZLE_128B smem tile -> ONE TMA bulk store per chunk (128-byte
+        // L2 requests instead of one 16-byte request per thread per store; rows >= M / columns >= N are clipped by tmC).
+        // Warp (q, grp) owns rows q*32 + lane and the grp-th 32 columns of the chunk.
+        const bool leader = threadIdx.x == 128;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c64 = ci * 64;
+          if (c64 >= t.n_valid) break;
+          const uint32_t obuf = out_base + (uint32_t)(ochunk & 1) * TC_OUT_BYTES;
+          ++ochunk;
+          if (leader) tma_wait_group_read1();       // the store that used this buffer two chunks ago has read it
+          named_bar_sync(1, 256);
+          const int c = c64 + grp * 32;
+          if (c < t.n_valid) {
+            const bool two = c + 32 <= t.n_valid;   // 32 columns, or a 16-column tail
+            uint32_t r[32];
+            if (two) tmem_ld32_nowait(taddr + c, r);
+            else tmem_ld16_nowait(taddr + c, r);
+            tmem_wait_ld();
+            if (row_ok) {
+              const uint32_t srow = obuf + (uint32_t)(q * 32 + lane) * 128u;
+              const int rx = lane & 7;
+#pragma unroll
+              for (int hblk = 0; hblk < 2; ++hblk) {
+                if (hblk == 1 && !two) break;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[hblk * 16 + i]) * p.alpha;
+                const int cc = c + hblk * 16;
+                if (p.bias) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + i);
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                  }
+                }
+                if (rv) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + cc + i));
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                  }
+                }
+                if (pre) {
+                  const uint4 r0 = rpre[4 * ci + 2 * hblk], r1 = rpre[4 * ci + 2 * hblk + 1];
+                  const __nv_bfloat162* e0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                  const __nv_bfloat162* e1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    v[2 * i] += __low2float(e0[i]); v[2 * i + 1] += __high2float(e0[i]);
+                    v[8 + 2 * i] += __low2float(e1[i]); v[8 + 2 * i + 1] += __high2float(e1[i]);
+                  }
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                  o[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                const int u = grp * 4 + hblk * 2;   // 16-byte unit of the 128-byte row, XOR-swizzled by the row
+                st_shared_v4(srow + (uint32_t)(((u) ^ rx) << 4), o[0], o[1], o[2], o[3]);
+                st_shared_v4(srow + (uint32_t)(((u + 1) ^ rx) << 4), o[4], o[5], o[6], o[7]);
+              }
+            }
+          }
+          fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(2, 256);
+          if (leader) {
+            tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0);
+            tma_commit_group();
+          }
+        }
+      } else if (fast) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int c = grp * 32 + ci * 64;
@@ -402,6 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (threadIdx.x == 128) tma_wait_group_read0();   // bulk stores must have read their staging tiles before smem goes away
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -495,17 +590,138 @@ static int pick_block_n(int n, bool mn_major) {
   return best;
 }
 
+// Cost model shared by the tiling choosers ("cycles" of one CTA): a 64-deep k-block of a 128 x w tile is bound either
+// by the MMA (2w) or by filling its 16 KB + w * 128 B of operands from L2 (~80 B/clk/SM when every SM streams), so
+// wide tiles are cheaper per column; plus the epilogue (~6w) and a fixed pipeline-fill / drain latency per tile.
+static inline double tile_cost(int w, int kb) {
+  const double mma = 2.0 * w, fill = 1.6 * (128 + w);
+  return kb * (mma > fill ? mma : fill) + 6.0 * w + 1500.0;
+}
+
+// Tile width for a [m_tiles x n] output on a persistent grid of g_num_sms CTAs: simulates the kernel's round-robin
+// tile -> CTA assignment (tile t = m_blk * n_tiles + n_blk goes to CTA t % grid) and keeps the width with the
+// smallest busiest-CTA load.  Two things the padding-only rule of pick_block_n misses: (1) N = 320 as 256 + 64 puts
+// every wide tile on the even CTAs and every narrow one on the odd CTAs (the grid size is even) - a 4:1 imbalance on
+// the most common GEMM of the 64x64 level - where 160 + 160 is balanced; (2) the 8x8 / 16x16 layers have 16-64 row
+// tiles, e.g. M=2048, N=1280: 80 tiles of 256 columns leave 68 SMs idle, 144 tiles of 144 columns do not.
+static int pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total) {
+  if (m_tiles <= 0 || m_tiles > 2048) return pick_block_n(n, mn_major);
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> memo;
+  const uint64_t key = ((uint64_t)n << 40) ^ ((uint64_t)kb_total << 16) ^ ((uint64_t)m_tiles << 1) ^ (mn_major ? 1u : 0u);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+  }
+  const int step = mn_major ? 64 : 16;
+  double best_cost = -1;
+  int best = 64;
+  std::vector<double> load(g_num_sms);
+  for (int bn = 256; bn >= 64; bn -= step) {
+    const int nt = (n + bn - 1) / bn;
+    const int last = n - (nt - 1) * bn;
+    const int last_pad = (last + step - 1) / step * step;
+    const long tiles = m_tiles * nt;
+    const int G = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    const double c_full = tile_cost(bn, kb_total), c_last = tile_cost(last_pad, kb_total);
+    std::fill(load.begin(), load.end(), 0.0);
+    for (long t = 0; t < tiles; ++t) load[t % G] += (t % nt) == nt - 1 ? c_last : c_full;
+    double cost = 0;
+    for (int i = 0; i < G; ++i) cost = load[i] > cost ? load[i] : cost;
+    if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best = bn; }
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = best;
+  return best;
+}
+
+// Split-K tilings (weight gradients: fp32 red.add epilogue).  Chooses the tile width AND the number of K splits by
+// simulating the persistent grid: tile t = ((m_blk * n_tiles) + n_blk) * splits + split runs on CTA t % grid and costs
+// tile_cost(w, kb).
+// `groups` x ceil(n / bn) N tiles per M tile (groups = 9 taps for the conv weight gradient).  The old rule aimed at
+// 2 x SMs tiles and often landed just above it (300 tiles = 3 rounds with 4 CTAs busy in the last one).
+struct SplitTiling { int bn, splits; };
+static SplitTiling pick_split_tiling(int n, int groups, long m_tiles, int kb_total) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, SplitTiling> memo;
+  const uint64_t key = ((uint64_t)n << 40) ^ ((uint64_t)groups << 36) ^ ((uint64_t)m_tiles << 24) ^ (uint64_t)kb_total;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+  }
+  SplitTiling best{pick_block_n(n, true), 1};
+  double best_cost = -1;
+  std::vector<double> load(g_num_sms);
+  int maxs = kb_total / 8;
+  if (maxs > 128) maxs = 128;
+  if (maxs < 1) maxs = 1;
+  for (int bn = 256; bn >= 64; bn -= 64) {
+    const int ntg = (n + bn - 1) / bn;
+    const int last_pad = (n - (ntg - 1) * bn + 63) / 64 * 64;
+    const long n_tiles = (long)groups * ntg;
+    const long base = m_tiles * n_tiles;
+    if (base > 4096) continue;
+    for (int sp = 1; sp <= maxs; ++sp) {
+      const long tiles = base * sp;
+      if (tiles > 16 * (long)g_num_sms && sp > 1) break;
+      const int per = (kb_total + sp - 1) / sp;
+      const int G = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+      std::fill(load.begin(), load.end(), 0.0);
+      for (long t = 0; t < tiles; ++t) {
+        const int split = (int)(t % sp);
+        const long r = t / sp;
+        const int nb = (int)(r % n_tiles);
+        const int w = (nb % ntg) == ntg - 1 ? last_pad : bn;
+        int kb = kb_total - split * per;
+        if (kb > per) kb = per;
+        if (kb <= 0) continue;
+        load[t % G] += tile_cost(w, kb);
+      }
+      double cost = 0;
+      for (int i = 0; i < G; ++i) cost = load[i] > cost ? load[i] : cost;
+      if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best = SplitTiling{bn, sp}; }
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = best;
+  return best;
+}
+
 long g_tc_launches = 0;
 thread_local int g_last_path = 0;   // 1 = the last GEMM/conv entry point of this thread ran on tcgen05
 extern long g_simt_launches;
 
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+// SIDLSG_TMA_STORE=0 keeps the per-row global stores of the epilogue (A/B switch for the staged TMA-store epilogue)
+static bool tma_store_enabled() {
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("SIDLSG_TMA_STORE");
+    state = (e && e[0] == '0') ? 0 : 1;
+  }
+  return state == 1;
+}
+
+// output map of the staged epilogue: bf16 [M rows][N columns], row stride ldc elements, box = 64 columns x 128 rows
+static bool make_out_map(CUtensorMap* m, TcParams& p, void* c, long M, long N, long ldc) {
+  p.tma_store = 0;
+  if (!tma_store_enabled() || p.out_f32 || p.atomic || p.batched || p.splits != 1) return true;
+  if ((ldc % 8) || (N % 8) || !aligned16(c)) return true;
+  uint64_t d[2] = {(uint64_t)N, (uint64_t)M}, s[1] = {(uint64_t)ldc * 2};
+  uint32_t bx[2] = {64, 128};
+  if (!make_map(m, c, 2, d, s, bx)) return false;
+  p.tma_store = 1;
+  return true;
+}
+
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, TcParams& p, cudaStream_t st) {
   long tiles = (long)p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
   if (tiles <= 0) return SIDLSG_OK;
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
   g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
 }
 
@@ -546,11 +762,17 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.cstride = 1;
-  p.block_n = pick_block_n(N, b_mn);
   p.m_tiles = (M + TC_BM - 1) / TC_BM;
-  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  p.block_n = (accumulate == 0 && nbatch == 1) ? pick_block_n_grid(N, b_mn, p.m_tiles, (K + TC_BK - 1) / TC_BK) : pick_block_n(N, b_mn);
   p.kb_total = (K + TC_BK - 1) / TC_BK;
-  p.splits = accumulate == 2 ? pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total) : 1;
+  p.splits = 1;
+  if (accumulate == 2 && nbatch == 1 && b_mn) {
+    const SplitTiling tl = pick_split_tiling(N, 1, p.m_tiles, p.kb_total);
+    p.block_n = tl.bn;
+    p.splits = tl.splits;
+  }
+  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  if (accumulate == 2 && !(nbatch == 1 && b_mn)) p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
   p.a_mode = a_k ? A_K2D : A_MN2D;
   p.b_mode = b_k ? B_K2D : B_MN2D;
   p.c = c; p.ldc = ldc; p.out_f32 = out_dtype == SIDLSG_F32;
@@ -569,7 +791,9 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
   };
   if (!dense_map(&ta, a, a_k, M, lda, a_sb1, a_sb2, 128)) return SIDLSG_ERR_CUDA;
   if (!dense_map(&tb, b, b_k, N, ldb, b_sb1, b_sb2, (uint32_t)p.block_n)) return SIDLSG_ERR_CUDA;
-  int r = launch_tc(ta, tb, p, st);
+  CUtensorMap tcm = ta;   // placeholder (a valid map) when the staged epilogue is not used
+  if (!make_out_map(&tcm, p, c, M, N, ldc)) return SIDLSG_ERR_CUDA;
+  int r = launch_tc(ta, tb, tcm, p, st);
   return r == SIDLSG_OK ? 1 : r;
 }
 
@@ -608,8 +832,8 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = N;
-  p.block_n = pick_block_n(N, dgrad);
   p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  p.block_n = pick_block_n_grid(N, dgrad, p.m_tiles, 9 * (Kc / 64));
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.splits = 1;
   p.cchunks = Kc / 64;
@@ -638,7 +862,9 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
     uint32_t bx[3] = {64, 1, 64};
     if (!make_map(&tb, w, 3, d, s, bx)) return SIDLSG_ERR_CUDA;
   }
-  int r = launch_tc(ta, tb, p, st);
+  CUtensorMap tcm = ta;
+  if (!make_out_map(&tcm, p, y, M, N, N)) return SIDLSG_ERR_CUDA;
+  int r = launch_tc(ta, tb, tcm, p, st);
   return r == SIDLSG_OK ? 1 : r;
 }
 
@@ -661,13 +887,14 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = Cout; p.N = 9 * Cin;
-  p.block_n = pick_block_n(Cin, true);
   p.m_tiles = (Cout + TC_BM - 1) / TC_BM;
+  p.kb_total = (int)(npix / 64);
+  const SplitTiling tl = pick_split_tiling(Cin, 9, p.m_tiles, p.kb_total);
+  p.block_n = tl.bn;
+  p.splits = tl.splits;
   p.n_tiles_per_tap = (Cin + p.block_n - 1) / p.block_n;
   p.n_tiles = 9 * p.n_tiles_per_tap;
   p.cin = Cin;
-  p.kb_total = (int)(npix / 64);
-  p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
   p.a_mode = A_MN2D;
   p.b_mode = B_CONV;
   p.H = Ho; p.W = Wo; p.cstride = stride;
@@ -686,7 +913,7 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
     uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     if (!make_map(&tb, x, 4, d, s, bx, es)) return SIDLSG_ERR_CUDA;
   }
-  int r = launch_tc(ta, tb, p, st);
+  int r = launch_tc(ta, tb, ta, p, st);
   return r == SIDLSG_OK ? 1 : r;
 }
 

@@ -69,6 +69,7 @@ gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partial, int HW, i
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
     if (v < vpr) {
+#pragma unroll 4
       for (int r = r0 + ty; r < r1; r += RY) {
         float e[V];
         gn_load<T, V>(xb + (long)r * C + v * V, e);
@@ -99,6 +100,7 @@ gn_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
   double s = 0, q = 0;
+#pragma unroll 4
   for (int i = lane; i < chunks * cpg; i += 32) {
     const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
     const float2 v = partial[((long)b * chunks + ch) * C + c];
@@ -174,7 +176,7 @@ gn_apply_rows_kernel(const T* __restrict__ x, const float* __restrict__ a, const
       av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
       sv[i] = s4.x; sv[i + 1] = s4.y; sv[i + 2] = s4.z; sv[i + 3] = s4.w;
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += RY) {
       float e[V];
       gn_load<T, V>(x + base + (long)r * C + v * V, e);
@@ -214,6 +216,7 @@ gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
       } else { av[i] = sv[i] = mu[i] = rs[i] = 0.f; }
     }
     if (v < vpr) {
+#pragma unroll 2
       for (int r = r0 + ty; r < r1; r += RY) {
         float xe[V], de[V];
         gn_load<T, V>(x + base + (long)r * C + v * V, xe);
@@ -250,6 +253,7 @@ gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restri
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
   double S1 = 0, S2 = 0;
+#pragma unroll 4
   for (int i = lane; i < chunks * cpg; i += 32) {
     const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
     const float2 v = partial[((long)b * chunks + ch) * C + c];
@@ -419,6 +423,147 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
   }
 }
 
+// ---- LayerNorm, vectorised (C % V == 0): lane l owns the 16-byte pieces l, l+32, ... of a row, so a warp reads a row
+// in 512-byte requests instead of 64-byte ones and gamma / beta live in registers across the warp's rows -----------------
+template <class T, int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int C,
+                  float eps) {
+  constexpr int V = GnVec<T>::n;
+  const int lane = threadIdx.x & 31;
+  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  const int pieces = C / V;
+  float gm[NV][V], bt[NV][V];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int p = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      gm[i][j] = p < pieces ? gamma[p * V + j] : 0.f;
+      bt[i][j] = p < pieces ? beta[p * V + j] : 0.f;
+    }
+  }
+  const float invC = 1.f / C;
+  for (long r = warp; r < rows; r += nwarps) {
+    const T* row = x + r * C;
+    float v[NV][V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pieces) gn_load<T, V>(row + p * V, v[i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) s += v[i][j];
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < pieces) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { const float dd = v[i][j] - mean; q = fmaf(dd, dd, q); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+    T* yr = y + r * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pieces) {
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gm[i][j], bt[i][j]);
+        gn_store<T, V>(yr + p * V, o);
+      }
+    }
+  }
+}
+
+template <class T, int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int C, int want_param_grad) {
+  extern __shared__ float red[];  // [2][C]
+  constexpr int V = GnVec<T>::n;
+  const int lane = threadIdx.x & 31;
+  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  const int pieces = C / V;
+  float gm[NV][V], dg[NV][V], db[NV][V];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int p = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      dg[i][j] = db[i][j] = 0.f;
+      gm[i][j] = p < pieces ? gamma[p * V + j] : 0.f;
+    }
+  }
+  const float invC = 1.f / C;
+  for (long r = warp; r < rows; r += nwarps) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[NV][V], g[NV][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pieces) {
+        float de[V];
+        gn_load<T, V>(dy + r * C + p * V, de);
+        gn_load<T, V>(x + r * C + p * V, xh[i]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          g[i][j] = de[j] * gm[i][j];
+          dg[i][j] = fmaf(de[j], xh[i][j], dg[i][j]);
+          db[i][j] += de[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) xh[i][j] = g[i][j] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int p = lane + 32 * i;
+      if (p < pieces) {
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        gn_store<T, V>(dx + r * C + p * V, o);
+      }
+    }
+  }
+  if (!want_param_grad) return;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int p = lane + 32 * i;
+    if (p < pieces) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { atomicAdd(&red[p * V + j], dg[i][j]); atomicAdd(&red[C + p * V + j], db[i][j]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], red[c]);
+    atomicAdd(&dbeta[c], red[C + c]);
+  }
+}
+
 }  // namespace sidlsg
 
 using namespace sidlsg;
@@ -505,6 +650,22 @@ extern "C" int sidlsg_layernorm_fwd(const void* x, const float* gamma, const flo
   int blocks = (int)((rows + 7) / 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
+  {
+    // vectorised kernels: slots = ceil(C / V / 32) in {1, 2, 3, 5, 10}
+    const int V = dtype == SIDLSG_F32 ? 4 : 8;
+    const int nv = (C % V) ? 0 : (C / V + 31) / 32;
+#define LN_FWD_V(T, NV) { ln_fwd_vec_kernel<T, NV><<<blocks, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, eps); return check_launch("layernorm_fwd"); }
+    if (nv >= 1 && nv <= 10 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+      if (dtype == SIDLSG_F32) {
+        if (nv <= 1) LN_FWD_V(float, 1) else if (nv <= 2) LN_FWD_V(float, 2) else if (nv <= 3) LN_FWD_V(float, 3)
+        else if (nv <= 5) LN_FWD_V(float, 5) else LN_FWD_V(float, 10)
+      } else {
+        if (nv <= 1) LN_FWD_V(bf16, 1) else if (nv <= 2) LN_FWD_V(bf16, 2) else if (nv <= 3) LN_FWD_V(bf16, 3)
+        else if (nv <= 5) LN_FWD_V(bf16, 5)
+      }
+    }
+#undef LN_FWD_V
+  }
 #define LN_FWD(T, NS) ln_fwd_kernel<T, NS><<<blocks, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, eps)
   if (dtype == SIDLSG_F32) { if (C <= 320) LN_FWD(float, 10); else if (C <= 640) LN_FWD(float, 20); else LN_FWD(float, 40); }
   else { if (C <= 320) LN_FWD(bf16, 10); else if (C <= 640) LN_FWD(bf16, 20); else LN_FWD(bf16, 40); }
@@ -519,10 +680,26 @@ extern "C" int sidlsg_layernorm_bwd(const void* dy, const void* x, const float* 
   if (C > 32 * LN_MAXSLOT_MAX) { set_error("layernorm_bwd: C=%d too large", C); return SIDLSG_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((rows + 7) / 8);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   int want = (dgamma && dbeta) ? 1 : 0;
   size_t sm = sizeof(float) * 2 * C;
+  {
+    const int V = dtype == SIDLSG_F32 ? 4 : 8;
+    const int nv = (C % V) ? 0 : (C / V + 31) / 32;
+#define LN_BWD_V(T, NV) { ln_bwd_vec_kernel<T, NV><<<blocks, 256, sm, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, C, want); return check_launch("layernorm_bwd"); }
+    if (nv >= 1 && nv <= 10 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+      if (dtype == SIDLSG_F32) {
+        if (nv <= 1) LN_BWD_V(float, 1) else if (nv <= 2) LN_BWD_V(float, 2) else if (nv <= 3) LN_BWD_V(float, 3)
+        else if (nv <= 5) LN_BWD_V(float, 5) else LN_BWD_V(float, 10)
+      } else {
+        if (nv <= 1) LN_BWD_V(bf16, 1) else if (nv <= 2) LN_BWD_V(bf16, 2) else if (nv <= 3) LN_BWD_V(bf16, 3)
+        else if (nv <= 5) LN_BWD_V(bf16, 5)
+      }
+    }
+#undef LN_BWD_V
+  }
 #define LN_BWD(T, NS) ln_bwd_kernel<T, NS><<<blocks, 256, sm, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, C, want)
   if (dtype == SIDLSG_F32) { if (C <= 320) LN_BWD(float, 10); else if (C <= 640) LN_BWD(float, 20); else LN_BWD(float, 40); }
   else { if (C <= 320) LN_BWD(bf16, 10); else if (C <= 640) LN_BWD(bf16, 20); else LN_BWD(bf16, 40); }

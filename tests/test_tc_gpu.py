@@ -46,7 +46,7 @@ class BfParam:
 
 
 @pytest.mark.parametrize("M,K,N", [(256, 64, 64), (4096, 320, 320), (1000, 768, 640), (512, 1280, 2560), (300, 640, 136),
-                                   (8192, 320, 960)])
+                                   (8192, 320, 960), (24576, 320, 320), (640, 320, 96), (384, 128, 80), (2048, 1280, 1280)])
 def test_tc_linear(M, K, N):
     g = torch.Generator().manual_seed(0)
     x = bf(torch.randn(M, K, generator=g))
@@ -73,7 +73,8 @@ def test_tc_linear(M, K, N):
 @pytest.mark.parametrize("B,H,C,N,stride", [(2, 16, 64, 64, 1), (1, 64, 64, 128, 1), (3, 32, 128, 64, 1),
                                             (4, 8, 320, 320, 1), (2, 16, 192, 320, 1), (1, 64, 320, 320, 1),
                                             (5, 8, 64, 192, 1), (2, 32, 64, 128, 2), (4, 16, 128, 128, 2),
-                                            (1, 64, 320, 320, 2), (3, 16, 64, 64, 2)])
+                                            (1, 64, 320, 320, 2), (3, 16, 64, 64, 2), (8, 64, 64, 128, 1),
+                                            (16, 8, 128, 320, 1)])
 def test_tc_conv3x3(B, H, C, N, stride):
     g = torch.Generator().manual_seed(1)
     x = bf(torch.randn(B, C, H, H, generator=g))
@@ -218,3 +219,51 @@ def test_packed_attention_matches_separate(B, N, M, C, heads, cross):
     check(dq, qs.grad, 2e-3, "dq")
     check(dk, ks.grad, 2e-3, "dk")
     check(dv, vs.grad, 2e-3, "dv")
+
+
+@pytest.mark.parametrize("rows,C", [(77, 32), (300, 320), (130, 640), (64, 1280), (5000, 320)])
+def test_bf16_layernorm(rows, C):
+    """vectorised LayerNorm kernels (16-byte pieces per lane) in the bf16 activation mode."""
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn(rows, C, generator=g) * 1.5 - 0.3)
+    ga = torch.randn(C, generator=g)
+    be = torch.randn(C, generator=g)
+    dy = bf(torch.randn(rows, C, generator=g))
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, ga, be))
+    yr = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    yr.backward(dy)
+    xd = x.to(DEV).bfloat16().requires_grad_(True)
+    gp = torch.nn.Parameter(ga.to(DEV)); gp.grad = torch.zeros_like(gp)
+    bp = torch.nn.Parameter(be.to(DEV)); bp.grad = torch.zeros_like(bp)
+    y = ops().layer_norm(xd, gp, bp, 1e-5)
+    y.backward(dy.to(DEV).bfloat16())
+    check(y, yr, 1.5e-2, "y")
+    check(xd.grad, xr.grad, 1.5e-2, "dx")
+    check(gp.grad, gr.grad, 2e-3, "dgamma")
+    check(bp.grad, br.grad, 2e-3, "dbeta")
+
+
+def test_tma_store_switch_matches():
+    """staged TMA-store epilogue == per-row store epilogue (bit-exact: same arithmetic, different way out)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from sid_lsg_b200 import ops\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "x = torch.randn(3000, 320, generator=g).cuda().bfloat16()\n"
+        "w = (torch.randn(960, 320, generator=g) / 18).cuda()\n"
+        "p = torch.nn.Parameter(w); p._shadow = w.bfloat16(); p.grad = torch.zeros_like(p)\n"
+        "b = torch.randn(960, generator=g).cuda()\n"
+        "r = torch.randn(3000, 960, generator=g).cuda().bfloat16()\n"
+        "y = ops.linear(x, p, b, r)\n"
+        "torch.cuda.synchronize(); print(float(y.float().double().sum()), float(y.float().abs().double().sum()))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, SIDLSG_TMA_STORE=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
