@@ -30,7 +30,8 @@ namespace sidlsg {
 enum { A_K2D = 0, A_MN2D = 1, A_CONV = 2 };
 enum { B_K2D = 0, B_MN2D = 1, B_W3D = 2, B_CONV = 3 };
 
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;          // ring depth with 256-column tiles; narrower tiles get more (p.stages, <= TC_MAX_STAGES)
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
@@ -65,6 +66,8 @@ struct TcParams {
   int rows_per_vec;
   float alpha;
   int atomic;               // fp32 red.add (split-K / gradient accumulation)
+  int stages;               // smem ring depth: floor(192 KB / (16 KB + B tile bytes)), 4..8
+  int stage_bytes;          // 16 KB A tile + B tile (block_n rows x 128 B, or 64-column boxes x 8 KB for MN-major B)
   int tma_store;            // bf16 output leaves through smem staging + TMA bulk stores (tmC) instead of per-row stores
   // batched dense GEMMs (attention score / value contractions per (batch, head)): 4-D operand maps
   // (inner, outer, nb2, nb1); tile index = ((batch * m_tiles) + m) * n_tiles + n
@@ -87,8 +90,15 @@ struct TileInfo {
 
 __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   TileInfo t;
-  int split = tile % p.splits;
-  int r = tile / p.splits;
+  // split-K tiles are ordered split-major: the CTAs running at the same time work on the SAME K slab for different
+  // (m, n) output tiles, so the operand slabs are fetched from HBM once and shared through L2 (with the split index
+  // innermost every concurrent CTA streamed its own slab: 300 MB of DRAM reads for 168 MB of operands)
+  int split = 0, r = tile;
+  if (p.splits > 1) {
+    const int base = p.m_tiles * p.n_tiles;
+    split = tile / base;
+    r = tile - split * base;
+  }
   int n_blk = r % p.n_tiles;
   int m_blk = r / p.n_tiles;
   t.b1 = t.b2 = 0;
@@ -125,10 +135,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_base = out_base + 2 * TC_OUT_BYTES;
   // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+  const int NST = p.stages;
+  const uint32_t STB = (uint32_t)p.stage_bytes;
   const uint32_t bias_base = bar_base + 256;          // float[256]: bias of the current tile's columns (staged epilogue)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -142,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     fence_barrier_init();
   }
@@ -171,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.a_mode == A_CONV) { ab0 = t.m0 / hw; ah0 = (t.m0 - ab0 * hw) / p.W; }
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * STB;
           const uint32_t sb = sa + TC_A_BYTES;
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, stage_tx);
@@ -216,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < b_boxes; ++j)
               tma_load_4d(&tmB, fb, sb + j * 8192, t.n_in + 64 * j, ox, bh0 * p.cstride + oy, bb0);
           }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -238,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * STB;
           const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
@@ -248,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             accumulate = 1;
           }
           tc_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         acc_phase[acc] ^= 1;
@@ -317,10 +329,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ci = 0; ci < 4; ++ci) {
           const int c64 = ci * 64;
           if (c64 >= t.n_valid) break;
+          // a partial chunk in the MIDDLE of a row (tile widths that are not multiples of 64, e.g. N = 320 as 160 + 160)
+          // cannot go through the 64-column box: the box would overwrite the neighbour tile's columns.  Those chunks
+          // leave through per-row stores; partial chunks at the end of the row are clipped by the tensor map.
+          const bool direct = (c64 + 64 > t.n_valid) && (t.col0 + t.n_valid < p.N);
           const uint32_t obuf = out_base + (uint32_t)(ochunk & 1) * TC_OUT_BYTES;
-          ++ochunk;
-          if (leader) tma_wait_group_read1();       // the store that used this buffer two chunks ago has read it
-          named_bar_sync(1, 256);
+          if (!direct) {
+            ++ochunk;
+            if (leader) tma_wait_group_read1();     // the store that used this buffer two chunks ago has read it
+            named_bar_sync(1, 256);
+          }
           const int c = c64 + grp * 32;
           if (c < t.n_valid) {
             const bool two = c + 32 <= t.n_valid;   // 32 columns, or a 16-column tail
@@ -368,17 +386,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                   o[i] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
-                const int u = grp * 4 + hblk * 2;   // 16-byte unit of the 128-byte row, XOR-swizzled by the row
-                st_shared_v4(srow + (uint32_t)(((u) ^ rx) << 4), o[0], o[1], o[2], o[3]);
-                st_shared_v4(srow + (uint32_t)(((u + 1) ^ rx) << 4), o[4], o[5], o[6], o[7]);
+                if (direct) {
+                  bf16* cp = reinterpret_cast<bf16*>(p.c) + crow + cc;
+                  *reinterpret_cast<uint4*>(cp) = make_uint4(o[0], o[1], o[2], o[3]);
+                  *reinterpret_cast<uint4*>(cp + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                } else {
+                  const int u = grp * 4 + hblk * 2;   // 16-byte unit of the 128-byte row, XOR-swizzled by the row
+                  st_shared_v4(srow + (uint32_t)(((u) ^ rx) << 4), o[0], o[1], o[2], o[3]);
+                  st_shared_v4(srow + (uint32_t)(((u + 1) ^ rx) << 4), o[4], o[5], o[6], o[7]);
+                }
               }
             }
           }
-          fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(2, 256);
-          if (leader) {
-            tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0);
-            tma_commit_group();
+          if (!direct) {
+            fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
+            named_bar_sync(2, 256);
+            if (leader) {
+              tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0);
+              tma_commit_group();
+            }
           }
         }
       } else if (fast) {
@@ -637,7 +663,7 @@ static int pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total) {
 }
 
 // Split-K tilings (weight gradients: fp32 red.add epilogue).  Chooses the tile width AND the number of K splits by
-// simulating the persistent grid: tile t = ((m_blk * n_tiles) + n_blk) * splits + split runs on CTA t % grid and costs
+// simulating the persistent grid: tile t = split * (m_tiles * n_tiles) + m_blk * n_tiles + n_blk runs on CTA t % grid and costs
 // tile_cost(w, kb).
 // `groups` x ceil(n / bn) N tiles per M tile (groups = 9 taps for the conv weight gradient).  The old rule aimed at
 // 2 x SMs tiles and often landed just above it (300 tiles = 3 rounds with 4 CTAs busy in the last one).
@@ -670,8 +696,8 @@ static SplitTiling pick_split_tiling(int n, int groups, long m_tiles, int kb_tot
       const int G = (int)(tiles < g_num_sms ? tiles : g_num_sms);
       std::fill(load.begin(), load.end(), 0.0);
       for (long t = 0; t < tiles; ++t) {
-        const int split = (int)(t % sp);
-        const long r = t / sp;
+        const int split = (int)(t / base);
+        const long r = t - split * base;
         const int nb = (int)(r % n_tiles);
         const int w = (nb % ntg) == ntg - 1 ? last_pad : bn;
         int kb = kb_total - split * per;
@@ -721,6 +747,15 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
   g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  {
+    // narrow tiles leave room for a deeper ring: K = 320 GEMMs (5 k-blocks per tile) then prefetch more than one
+    // whole tile ahead while the epilogue of the previous tile drains
+    const bool b_mn = p.b_mode != B_K2D;
+    const int b_bytes = b_mn ? ((p.block_n + 63) >> 6) * 8192 : p.block_n * 128;
+    p.stage_bytes = TC_A_BYTES + b_bytes;
+    int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;
+    p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < TC_STAGES ? TC_STAGES : ns);
+  }
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
 }

@@ -69,7 +69,6 @@ gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partial, int HW, i
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
     if (v < vpr) {
-#pragma unroll 4
       for (int r = r0 + ty; r < r1; r += RY) {
         float e[V];
         gn_load<T, V>(xb + (long)r * C + v * V, e);
@@ -100,7 +99,6 @@ gn_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
   double s = 0, q = 0;
-#pragma unroll 4
   for (int i = lane; i < chunks * cpg; i += 32) {
     const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
     const float2 v = partial[((long)b * chunks + ch) * C + c];
@@ -176,7 +174,7 @@ gn_apply_rows_kernel(const T* __restrict__ x, const float* __restrict__ a, const
       av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
       sv[i] = s4.x; sv[i + 1] = s4.y; sv[i + 2] = s4.z; sv[i + 3] = s4.w;
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int r = r0 + ty; r < r1; r += RY) {
       float e[V];
       gn_load<T, V>(x + base + (long)r * C + v * V, e);
@@ -216,7 +214,6 @@ gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
       } else { av[i] = sv[i] = mu[i] = rs[i] = 0.f; }
     }
     if (v < vpr) {
-#pragma unroll 2
       for (int r = r0 + ty; r < r1; r += RY) {
         float xe[V], de[V];
         gn_load<T, V>(x + base + (long)r * C + v * V, xe);
@@ -253,7 +250,6 @@ gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restri
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
   double S1 = 0, S2 = 0;
-#pragma unroll 4
   for (int i = lane; i < chunks * cpg; i += 32) {
     const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
     const float2 v = partial[((long)b * chunks + ch) * C + c];
