@@ -10,6 +10,7 @@ tests) timeout 1200 python -m pytest tests -m gpu -q --maxfail=12 -p no:cachepro
 smoke) timeout 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
 bench) timeout 1500 python bench.py --shapes $OUT/shapes.txt > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json;;
 benchq) timeout 1500 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/shapes.txt > $OUT/bench.json 2> $OUT/bench.err; tail -c 1500 $OUT/bench.err; python scripts/bench_brief.py $OUT/bench.json;;
+benchmb) timeout 900 python bench.py --no-cpu-baseline --steps 3 --batch-gpu ${MB:-32} --shapes $OUT/shapes_mb.txt > $OUT/bench_mb.json 2> $OUT/bench_mb.err; tail -c 800 $OUT/bench_mb.err; python scripts/bench_brief.py $OUT/bench_mb.json;;
 list) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
         python bench.py --batch 16 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-roofline > $OUT/list_bench.log 2>&1
       python scripts/ncu_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; rm -f $OUT/launches.csv.keep
