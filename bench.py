@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per iteration")
-    ap.add_argument("--batch-gpu", type=int, default=16, help="micro-batch (gradient accumulation rounds = batch / batch-gpu)")
+    ap.add_argument("--batch-gpu", type=int, default=32, help="micro-batch (gradient accumulation rounds = batch / batch-gpu)")
     ap.add_argument("--kappa", type=float, default=1.5)
     ap.add_argument("--num-steps", type=int, default=1, help="generator sub-steps (config 5 uses 4)")
     ap.add_argument("--model", default="SD15", choices=["SD15", "SD21_BASE", "TINY"])

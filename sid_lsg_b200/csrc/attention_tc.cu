@@ -346,10 +346,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Forward, second generation (d <= 128): 64-key tiles with TWO score buffers in TMEM, so the MMA warp runs one tile
-// ahead of the softmax warps - S_{j+1} = Q K_{j+1}^T is issued while the exponentials of tile j are still running and
-// the softmax warps never wait for the tensor pipe (in the 128-key single-buffer kernel above they sat idle during
-// every P V + Q K^T round trip: MUFU pipe 46 % busy in ncu).  TMEM: S0 | S1 (64 columns each) | O (<= 128) = 256
+// Forward, experimental variant (d <= 128, SIDLSG_ATTN_FWD_V2=1): 64-key tiles with TWO score buffers in TMEM, so the
+// MMA warp runs one tile ahead of the softmax warps - S_{j+1} = Q K_{j+1}^T is issued while the exponentials of tile j
+// are still running and the softmax warps never wait for the tensor pipe.  Correct (parity tests) but 13 % SLOWER than
+// the 128-key kernel above on B200, which shows that kernel is not stalled on the MMA round trip.  TMEM: S0 | S1 (64 columns each) | O (<= 128) = 256
 // columns, two CTAs per SM for d <= 64 as before.  P is double buffered in shared memory ([128 x 64] bf16 each).
 //   MMA issue order: QK(0) QK(1) PV(0) QK(2) PV(1) QK(3) ...   (QK(j+2) reuses S[j&1], free once P_j has been written)
 //   barriers: s_full[2] (MMA -> softmax), p_full[2] (softmax -> MMA, 4 warp arrivals), p_free[2] (P_j V_j retired: the
@@ -667,8 +667,11 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = (bf16*)o; p.lse = lse;
   CUtensorMap tq, tk, tv;
-  static int fwd_gen = -1;   // SIDLSG_ATTN_FWD_V1=1 keeps the 128-key single-buffer kernel (A/B switch)
-  if (fwd_gen < 0) { const char* e = getenv("SIDLSG_ATTN_FWD_V1"); fwd_gen = (e && e[0] == '1') ? 1 : 2; }
+  // SIDLSG_ATTN_FWD_V2=1 selects the 64-key double-buffered kernel.  Measured on B200 (B8 N4096 d40): 0.632 ms vs
+  // 0.558 ms for the 128-key kernel - the softmax loop is bound by its own MUFU / TMEM-read / issue work, not by waiting
+  // for the tensor pipe, so halving the tile only doubles the per-tile barrier cost.  Kept as a tested A/B variant.
+  static int fwd_gen = -1;
+  if (fwd_gen < 0) { const char* e = getenv("SIDLSG_ATTN_FWD_V2"); fwd_gen = (e && e[0] == '1') ? 2 : 1; }
   if (fwd_gen == 2 && p.dpad <= 128) {
     if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk, A2_BKV) ||
         !make_head_map(&tv, v, d, H, M, B, ldv, A2_BKV))

@@ -66,6 +66,7 @@ struct TcParams {
   int rows_per_vec;
   float alpha;
   int atomic;               // fp32 red.add (split-K / gradient accumulation)
+  int bm2;                  // 256-row tiles: two 128-row A tiles share every B tile (two accumulators, single-buffered)
   int stages;               // smem ring depth: floor(192 KB / (16 KB + B tile bytes)), 4..8
   int stage_bytes;          // 16 KB A tile + B tile (block_n rows x 128 B, or 64-column boxes x 8 KB for MN-major B)
   int tma_store;            // bf16 output leaves through smem staging + TMA bulk stores (tmC) instead of per-row stores
@@ -108,7 +109,7 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
     t.b1 = bidx / p.nb2;
     t.b2 = bidx - t.b1 * p.nb2;
   }
-  t.m0 = m_blk * TC_BM;
+  t.m0 = m_blk * (p.bm2 ? 2 * TC_BM : TC_BM);
   if (p.b_mode == B_CONV) {
     t.tap = n_blk / p.n_tiles_per_tap;
     t.n_in = (n_blk - t.tap * p.n_tiles_per_tap) * p.block_n;
@@ -169,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_mn = p.a_mode == A_MN2D;
   const int b_mn = p.b_mode != B_K2D;
   const int b_boxes = (p.block_n + 63) >> 6;
-  const uint32_t stage_tx = TC_A_BYTES + (b_mn ? b_boxes * 8192 : p.block_n * 128);
+  const uint32_t a_bytes = p.bm2 ? 2 * TC_A_BYTES : TC_A_BYTES;
+  const uint32_t stage_tx = a_bytes + (b_mn ? b_boxes * 8192 : p.block_n * 128);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -179,12 +181,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int hw = p.H * p.W;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
-        int ab0 = 0, ah0 = 0;
-        if (p.a_mode == A_CONV) { ab0 = t.m0 / hw; ah0 = (t.m0 - ab0 * hw) / p.W; }
+        int ab0 = 0, ah0 = 0, ab1 = 0, ah1 = 0;
+        if (p.a_mode == A_CONV) {
+          ab0 = t.m0 / hw; ah0 = (t.m0 - ab0 * hw) / p.W;
+          ab1 = (t.m0 + TC_BM) / hw; ah1 = (t.m0 + TC_BM - ab1 * hw) / p.W;   // second 128-pixel box (bm2)
+        }
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STB;
-          const uint32_t sb = sa + TC_A_BYTES;
+          const uint32_t sb = sa + a_bytes;
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, stage_tx);
           int tap = 0, c0 = kb * TC_BK;
@@ -199,6 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else if (p.a_mode == A_K2D) {
             tma_load_2d(&tmA, fb, sa, kb * TC_BK, t.m0);
+            if (p.bm2) tma_load_2d(&tmA, fb, sa + TC_A_BYTES, kb * TC_BK, t.m0 + TC_BM);
           } else if (p.a_mode == A_MN2D) {
             tma_load_2d(&tmA, fb, sa, t.m0, kb * TC_BK);
             tma_load_2d(&tmA, fb, sa + 8192, t.m0 + 64, kb * TC_BK);
@@ -206,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int oy = tap / 3 - 1, ox = tap % 3 - 1;
             if (p.flip) { oy = -oy; ox = -ox; }
             tma_load_4d(&tmA, fb, sa, c0, ox, ah0 * p.cstride + oy, ab0);
+            if (p.bm2) tma_load_4d(&tmA, fb, sa + TC_A_BYTES, c0, ox, ah1 * p.cstride + oy, ab1);
           }
           // ---- B ----
           if (p.batched) {
@@ -251,12 +258,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STB;
-          const uint32_t sb = sa + TC_A_BYTES;
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t ad = a_mn ? make_desc(sa + k * 2048, 1024, 8192) : make_desc(sa + k * 32, 1024, 0);
             const uint64_t bd = b_mn ? make_desc(sb + k * 2048, 1024, 8192) : make_desc(sb + k * 32, 1024, 0);
             tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+            // bm2: rows 128..255 of the tile (second A tile, K-major only) against the SAME B tile -> columns 256.. of TMEM
+            if (p.bm2) tc_mma_bf16(d_tmem + 256, make_desc(sa + TC_A_BYTES + k * 32, 1024, 0), bd, idesc, accumulate);
             accumulate = 1;
           }
           tc_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
@@ -264,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         acc_phase[acc] ^= 1;
-        acc ^= 1;
+        if (!p.bm2) acc ^= 1;            // bm2: both TMEM halves belong to one tile (single-buffered)
       }
     }
   } else if (warp >= 4) {
@@ -277,10 +286,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
-      const int m = t.m0 + q * 32 + lane;
+      const int nhalf = p.bm2 ? 2 : 1;
+      for (int half = 0; half < nhalf; ++half) {     // bm2: rows 0-127 (TMEM columns 0..) then rows 128-255 (columns 256..)
+      const int m = t.m0 + half * TC_BM + q * 32 + lane;
       const bool row_ok = m < p.M;
       const bool has_work = t.kb1 > t.kb0;
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (acc + half) * 256 + ((uint32_t)(q * 32) << 16);
       const long crow = (long)m * p.ldc + t.col0 + t.b1 * p.c_sb1 + t.b2 * p.c_sb2;
       const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long)(m / p.rows_per_vec) * p.N + t.col0 : nullptr;
       // fast path: whole 16-column groups, 16-byte aligned rows (every shape of the UNet)
@@ -311,20 +322,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const bool ts = fast && p.tma_store;        // uniform over the 8 epilogue warps (depends on the tile only)
-      if (ts && p.bias) {
+      if (ts && p.bias && half == 0) {
         // bias of this tile's columns -> smem while the main loop is still running (the per-chunk __ldg's were the
         // epilogue's largest stall).  Single buffer: every read of the previous tile's bias precedes that tile's last
         // named barrier, every read of this one follows the first barrier below.
         const int j = threadIdx.x - 128;
         if (j < t.n_valid) bias_s[j] = __ldg(p.bias + t.col0 + j);
       }
-      mbar_wait(tfull_bar(acc), acc_phase[acc]);
-      tc_fence_after();
+      if (half == 0) {
+        mbar_wait(tfull_bar(acc), acc_phase[acc]);
+        tc_fence_after();
+      }
       if (ts) {
         // ---- staged epilogue: 64-column chunks -> bf16 SWIZZLE_128B smem tile -> ONE TMA bulk store per chunk (128-byte
         // L2 requests instead of one 16-byte request per thread per store; rows >= M / columns >= N are clipped by tmC).
         // Warp (q, grp) owns rows q*32 + lane and the grp-th 32 columns of the chunk.
         const bool leader = threadIdx.x == 128;
+        bool tail_direct = false;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int c64 = ci * 64;
@@ -333,6 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // cannot go through the 64-column box: the box would overwrite the neighbour tile's columns.  Those chunks
           // leave through per-row stores; partial chunks at the end of the row are clipped by the tensor map.
           const bool direct = (c64 + 64 > t.n_valid) && (t.col0 + t.n_valid < p.N);
+          tail_direct = direct;
           const uint32_t obuf = out_base + (uint32_t)(ochunk & 1) * TC_OUT_BYTES;
           if (!direct) {
             ++ochunk;
@@ -402,11 +417,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
             named_bar_sync(2, 256);
             if (leader) {
-              tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0);
+              tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0 + half * TC_BM);
               tma_commit_group();
             }
           }
         }
+        // a direct tail chunk has no barrier behind it: without this one a fast warp could stage the NEXT tile's bias
+        // while a slow warp still reads this tile's
+        if (tail_direct && p.bias) named_bar_sync(1, 256);
       } else if (fast) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -514,11 +532,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }   // half
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc_phase[acc] ^= 1;
-      acc ^= 1;
+      if (!p.bm2) acc ^= 1;
     }
   }
 
@@ -616,12 +635,16 @@ static int pick_block_n(int n, bool mn_major) {
   return best;
 }
 
-// Cost model shared by the tiling choosers ("cycles" of one CTA): a 64-deep k-block of a 128 x w tile is bound either
-// by the MMA (2w) or by filling its 16 KB + w * 128 B of operands from L2 (~80 B/clk/SM when every SM streams), so
-// wide tiles are cheaper per column; plus the epilogue (~6w) and a fixed pipeline-fill / drain latency per tile.
-static inline double tile_cost(int w, int kb) {
-  const double mma = 2.0 * w, fill = 1.6 * (128 + w);
-  return kb * (mma > fill ? mma : fill) + 6.0 * w + 1500.0;
+// Cost model shared by the tiling choosers ("cycles" of one CTA).  Measured with ncu on the 3x3 convolutions: every
+// SM receives ~42 B/clk from L2 when all of them stream (the chip-wide L2 -> SM cap), so a 64-deep k-block of a 128 x w
+// tile costs max(MMA = 2w, fill = (16 KB + 128 w) / 42) - fill-bound at every width, wide tiles cheaper per column.
+// A 256-row tile (bm2: two A tiles against one B tile) moves (32 KB + 128 w) per 4w MMA cycles: 1.4-1.5x fewer bytes
+// per FLOP, but its two accumulators fill TMEM, so its epilogue is not hidden behind the next main loop.
+static inline double tile_cost(int w, int kb, bool bm2 = false) {
+  const double mma = (bm2 ? 4.0 : 2.0) * w;
+  const double fill = ((bm2 ? 32768.0 : 16384.0) + 128.0 * w) / 42.0;
+  const double epi = bm2 ? 2.0 * (8.0 * w + 600.0) : 6.0 * w;
+  return kb * (mma > fill ? mma : fill) + epi + 1500.0;
 }
 
 // Tile width for a [m_tiles x n] output on a persistent grid of g_num_sms CTAs: simulates the kernel's round-robin
@@ -630,11 +653,16 @@ static inline double tile_cost(int w, int kb) {
 // every wide tile on the even CTAs and every narrow one on the odd CTAs (the grid size is even) - a 4:1 imbalance on
 // the most common GEMM of the 64x64 level - where 160 + 160 is balanced; (2) the 8x8 / 16x16 layers have 16-64 row
 // tiles, e.g. M=2048, N=1280: 80 tiles of 256 columns leave 68 SMs idle, 144 tiles of 144 columns do not.
-static int pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total) {
-  if (m_tiles <= 0 || m_tiles > 2048) return pick_block_n(n, mn_major);
+struct GridTiling { int bn; double cost; };
+static GridTiling pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total, bool bm2 = false) {
+  if (m_tiles <= 0 || m_tiles > 2048) {
+    const int bn = pick_block_n(n, mn_major);
+    return GridTiling{bn, (double)m_tiles * ((n + bn - 1) / bn) * tile_cost(bn, kb_total, bm2) / g_num_sms};
+  }
   static std::mutex mu;
-  static std::unordered_map<uint64_t, int> memo;
-  const uint64_t key = ((uint64_t)n << 40) ^ ((uint64_t)kb_total << 16) ^ ((uint64_t)m_tiles << 1) ^ (mn_major ? 1u : 0u);
+  static std::unordered_map<uint64_t, GridTiling> memo;
+  const uint64_t key = ((uint64_t)n << 40) ^ ((uint64_t)kb_total << 16) ^ ((uint64_t)m_tiles << 2) ^ (bm2 ? 2u : 0u) ^
+                       (mn_major ? 1u : 0u);
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);
@@ -650,7 +678,7 @@ static int pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total) {
     const int last_pad = (last + step - 1) / step * step;
     const long tiles = m_tiles * nt;
     const int G = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    const double c_full = tile_cost(bn, kb_total), c_last = tile_cost(last_pad, kb_total);
+    const double c_full = tile_cost(bn, kb_total, bm2), c_last = tile_cost(last_pad, kb_total, bm2);
     std::fill(load.begin(), load.end(), 0.0);
     for (long t = 0; t < tiles; ++t) load[t % G] += (t % nt) == nt - 1 ? c_last : c_full;
     double cost = 0;
@@ -658,8 +686,18 @@ static int pick_block_n_grid(int n, bool mn_major, long m_tiles, int kb_total) {
     if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
   std::lock_guard<std::mutex> lk(mu);
-  memo[key] = best;
-  return best;
+  memo[key] = GridTiling{best, best_cost};
+  return memo[key];
+}
+
+// SIDLSG_BM2=0 disables the 256-row tiles, =2 forces them wherever the kernel can run them (tests), default = cost model
+static int bm2_mode() {
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("SIDLSG_BM2");
+    state = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);
+  }
+  return state;
 }
 
 // Split-K tilings (weight gradients: fp32 red.add epilogue).  Chooses the tile width AND the number of K splits by
@@ -752,9 +790,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     // whole tile ahead while the epilogue of the previous tile drains
     const bool b_mn = p.b_mode != B_K2D;
     const int b_bytes = b_mn ? ((p.block_n + 63) >> 6) * 8192 : p.block_n * 128;
-    p.stage_bytes = TC_A_BYTES + b_bytes;
-    int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;
-    p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < TC_STAGES ? TC_STAGES : ns);
+    p.stage_bytes = (p.bm2 ? 2 : 1) * TC_A_BYTES + b_bytes;
+    int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;     // what fits in the 192 KB ring
+    p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < 2 ? 2 : ns);
   }
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
@@ -798,7 +836,19 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.cstride = 1;
   p.m_tiles = (M + TC_BM - 1) / TC_BM;
-  p.block_n = (accumulate == 0 && nbatch == 1) ? pick_block_n_grid(N, b_mn, p.m_tiles, (K + TC_BK - 1) / TC_BK) : pick_block_n(N, b_mn);
+  p.block_n = pick_block_n(N, b_mn);
+  if (accumulate == 0 && nbatch == 1) {
+    const int kbt = (K + TC_BK - 1) / TC_BK;
+    const GridTiling t1 = pick_block_n_grid(N, b_mn, p.m_tiles, kbt);
+    p.block_n = t1.bn;
+    // 256-row tiles for the L2-bound (deep-K) GEMMs with enough rows to keep every SM busy
+    const int mode = bm2_mode();
+    if (mode && a_k && out_dtype == SIDLSG_BF16 && ((kbt >= 16 && M >= 512) || (mode == 2 && M >= 256))) {
+      const long mt2 = (M + 2 * TC_BM - 1) / (2 * TC_BM);
+      const GridTiling t2 = pick_block_n_grid(N, b_mn, mt2, kbt, true);
+      if (mode == 2 || t2.cost < t1.cost * 0.95) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
+    }
+  }
   p.kb_total = (K + TC_BK - 1) / TC_BK;
   p.splits = 1;
   if (accumulate == 2 && nbatch == 1 && b_mn) {
@@ -868,7 +918,17 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = N;
   p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
-  p.block_n = pick_block_n_grid(N, dgrad, p.m_tiles, 9 * (Kc / 64));
+  {
+    const int kbt = 9 * (Kc / 64);
+    const GridTiling t1 = pick_block_n_grid(N, dgrad, p.m_tiles, kbt);
+    p.block_n = t1.bn;
+    const int mode = bm2_mode();
+    if (mode && M >= 256 && (M % (2 * TC_BM)) == 0) {
+      const long mt2 = M / (2 * TC_BM);
+      const GridTiling t2 = pick_block_n_grid(N, dgrad, mt2, kbt, true);
+      if (mode == 2 || (M >= 512 && t2.cost < t1.cost * 0.95)) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
+    }
+  }
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.splits = 1;
   p.cchunks = Kc / 64;

@@ -267,3 +267,70 @@ def test_tma_store_switch_matches():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1], outs
+
+
+def test_attention_fwd_v2_switch():
+    """the 64-key double-buffered forward (SIDLSG_ATTN_FWD_V2=1) agrees with the default kernel."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from sid_lsg_b200 import ops\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "q = torch.randn(2, 1024, 320, generator=g).cuda().bfloat16()\n"
+        "k = torch.randn(2, 333, 320, generator=g).cuda().bfloat16()\n"
+        "v = torch.randn(2, 333, 320, generator=g).cuda().bfloat16()\n"
+        "o = ops.attention(q, k, v, 8)\n"
+        "torch.cuda.synchronize(); print(float(o.float().double().sum()), float(o.float().abs().double().sum()))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, SIDLSG_ATTN_FWD_V2=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([float(x) for x in r.stdout.strip().splitlines()[-1].split()])
+    assert abs(outs[0][1] - outs[1][1]) <= 2e-3 * abs(outs[0][1]), outs
+    assert abs(outs[0][0] - outs[1][0]) <= 2e-3 * abs(outs[0][1]), outs
+
+
+def test_bm2_tiles_match():
+    """256-row tiles (two A tiles per B tile, SIDLSG_BM2=2 forces them) == 128-row tiles, bit for bit: the reduction
+    order of every output element is the same, only the tile shape differs."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys, math; sys.path.insert(0, %r)\n"
+        "from sid_lsg_b200 import ops\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "def P(t, cl=False):\n"
+        "    t = t.cuda()\n"
+        "    if cl: t = t.contiguous(memory_format=torch.channels_last)\n"
+        "    p = torch.nn.Parameter(t); p._shadow = p.detach().bfloat16(); p.grad = torch.zeros_like(p); return p\n"
+        "out = []\n"
+        "for (M, K, N) in ((1000, 1280, 320), (4096, 2560, 640), (512, 320, 960), (2304, 640, 136)):\n"
+        "    x = torch.randn(M, K, generator=g).cuda().bfloat16().requires_grad_(True)\n"
+        "    w = P(torch.randn(N, K, generator=g) / math.sqrt(K))\n"
+        "    b = torch.randn(N, generator=g).cuda()\n"
+        "    r = torch.randn(M, N, generator=g).cuda().bfloat16()\n"
+        "    y = ops.linear(x, w, b, r)\n"
+        "    y.backward(torch.randn(M, N, generator=g).cuda().bfloat16())\n"
+        "    out += [y.float().double().sum().item(), y.float().abs().double().sum().item(), x.grad.float().abs().double().sum().item()]\n"
+        "for (B, H, C, N, st) in ((4, 16, 128, 320, 1), (2, 32, 64, 128, 2), (8, 8, 320, 192, 1)):\n"
+        "    x = torch.randn(B, H, H, C, generator=g).cuda().bfloat16().requires_grad_(True)\n"
+        "    w = P(torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C), True)\n"
+        "    b = torch.randn(N, generator=g).cuda()\n"
+        "    rv = torch.randn(B, N, generator=g).cuda()\n"
+        "    y = ops.conv3x3(x, w, b, None, rv, st)\n"
+        "    y.backward(torch.randn(y.shape, generator=g).cuda().bfloat16())\n"
+        "    out += [y.float().double().sum().item(), y.float().abs().double().sum().item(), x.grad.float().abs().double().sum().item()]\n"
+        "torch.cuda.synchronize(); print(' '.join(repr(v) for v in out))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "2"):
+        env = dict(os.environ, SIDLSG_BM2=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
