@@ -127,6 +127,7 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   return t;
 }
 
+template <bool BM2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -170,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_mn = p.a_mode == A_MN2D;
   const int b_mn = p.b_mode != B_K2D;
   const int b_boxes = (p.block_n + 63) >> 6;
-  const uint32_t a_bytes = p.bm2 ? 2 * TC_A_BYTES : TC_A_BYTES;
+  const uint32_t a_bytes = BM2 ? 2 * TC_A_BYTES : TC_A_BYTES;
   const uint32_t stage_tx = a_bytes + (b_mn ? b_boxes * 8192 : p.block_n * 128);
 
   if (warp == 0) {
@@ -204,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else if (p.a_mode == A_K2D) {
             tma_load_2d(&tmA, fb, sa, kb * TC_BK, t.m0);
-            if (p.bm2) tma_load_2d(&tmA, fb, sa + TC_A_BYTES, kb * TC_BK, t.m0 + TC_BM);
+            if (BM2) tma_load_2d(&tmA, fb, sa + TC_A_BYTES, kb * TC_BK, t.m0 + TC_BM);
           } else if (p.a_mode == A_MN2D) {
             tma_load_2d(&tmA, fb, sa, t.m0, kb * TC_BK);
             tma_load_2d(&tmA, fb, sa + 8192, t.m0 + 64, kb * TC_BK);
@@ -212,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int oy = tap / 3 - 1, ox = tap % 3 - 1;
             if (p.flip) { oy = -oy; ox = -ox; }
             tma_load_4d(&tmA, fb, sa, c0, ox, ah0 * p.cstride + oy, ab0);
-            if (p.bm2) tma_load_4d(&tmA, fb, sa + TC_A_BYTES, c0, ox, ah1 * p.cstride + oy, ab1);
+            if (BM2) tma_load_4d(&tmA, fb, sa + TC_A_BYTES, c0, ox, ah1 * p.cstride + oy, ab1);
           }
           // ---- B ----
           if (p.batched) {
@@ -265,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bd = b_mn ? make_desc(sb + k * 2048, 1024, 8192) : make_desc(sb + k * 32, 1024, 0);
             tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
             // bm2: rows 128..255 of the tile (second A tile, K-major only) against the SAME B tile -> columns 256.. of TMEM
-            if (p.bm2) tc_mma_bf16(d_tmem + 256, make_desc(sa + TC_A_BYTES + k * 32, 1024, 0), bd, idesc, accumulate);
+            if (BM2) tc_mma_bf16(d_tmem + 256, make_desc(sa + TC_A_BYTES + k * 32, 1024, 0), bd, idesc, accumulate);
             accumulate = 1;
           }
           tc_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
@@ -273,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         acc_phase[acc] ^= 1;
-        if (!p.bm2) acc ^= 1;            // bm2: both TMEM halves belong to one tile (single-buffered)
+        if (!BM2) acc ^= 1;            // bm2: both TMEM halves belong to one tile (single-buffered)
       }
     }
   } else if (warp >= 4) {
@@ -286,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
-      const int nhalf = p.bm2 ? 2 : 1;
+      const int nhalf = BM2 ? 2 : 1;
       for (int half = 0; half < nhalf; ++half) {     // bm2: rows 0-127 (TMEM columns 0..) then rows 128-255 (columns 256..)
       const int m = t.m0 + half * TC_BM + q * 32 + lane;
       const bool row_ok = m < p.M;
@@ -537,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc_phase[acc] ^= 1;
-      if (!p.bm2) acc ^= 1;
+      if (!BM2) acc ^= 1;
     }
   }
 
@@ -610,7 +611,8 @@ bool tc_enabled() {
               cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10 && get_encode() != nullptr;
     if (ok) {
       g_num_sms = prop.multiProcessorCount;
-      ok = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+      ok = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     }
     cudaGetLastError();
     g_tc_state = ok ? 1 : 0;
@@ -794,7 +796,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;     // what fits in the 192 KB ring
     p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < 2 ? 2 : ns);
   }
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
+  if (p.bm2) gemm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
+  else gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
 }
 
@@ -843,7 +846,9 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
     p.block_n = t1.bn;
     // 256-row tiles for the L2-bound (deep-K) GEMMs with enough rows to keep every SM busy
     const int mode = bm2_mode();
-    if (mode && a_k && out_dtype == SIDLSG_BF16 && ((kbt >= 16 && M >= 512) || (mode == 2 && M >= 256))) {
+    static int min_kb = -1;   // SIDLSG_BM2_MINKB: shallowest reduction (in 64-element blocks) that gets 256-row tiles
+    if (min_kb < 0) { const char* e = getenv("SIDLSG_BM2_MINKB"); min_kb = e ? atoi(e) : 16; if (min_kb < 1) min_kb = 1; }
+    if (mode && a_k && out_dtype == SIDLSG_BF16 && ((kbt >= min_kb && M >= 512) || (mode == 2 && M >= 256))) {
       const long mt2 = (M + 2 * TC_BM - 1) / (2 * TC_BM);
       const GridTiling t2 = pick_block_n_grid(N, b_mn, mt2, kbt, true);
       if (mode == 2 || t2.cost < t1.cost * 0.95) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
