@@ -29,6 +29,7 @@ struct AttnParams {
   float scale, scale_log2;
   bf16* o;
   float* lse;
+  unsigned wait_hint;    // ns, helper-warp mbarrier waits (tc_wait_hint_ns)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -112,7 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < T; ++j) {
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
-        mbar_wait(kv_empty(st), ph ^ 1);
+        mbar_wait_h(p.wait_hint, kv_empty(st), ph ^ 1);
         mbar_expect_tx(k_full(st), tile_bytes);
         for (int c = 0; c < p.dchunks; ++c)
           tma_load_4d(&tmK, k_full(st), k_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, j * AT_BKV, b);
@@ -135,8 +136,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_mma_bf16(s_tmem, make_desc(q_smem + off, 1024, 0), make_desc(kb + off, 1024, 0), idesc, s > 0);
         }
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full(0), 0);
+      mbar_wait_h(p.wait_hint, q_full, 0);
+      mbar_wait_h(p.wait_hint, k_full(0), 0);
       tc_fence_after();
       issue_qk(0);
       tc_commit(s_full);
@@ -145,8 +146,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
         const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
-        mbar_wait(p_full, j & 1);
-        mbar_wait(v_full(st), ph);
+        mbar_wait_h(p.wait_hint, p_full, j & 1);
+        mbar_wait_h(p.wait_hint, v_full(st), ph);
         tc_fence_after();
         const uint32_t vb = v_smem + st * tile_bytes;
         const int ksteps = (n_valid + 15) >> 4;
@@ -158,7 +159,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_commit(o_full);
         if (j + 1 < T) {
           const int st2 = (j + 1) % ST;
-          mbar_wait(k_full(st2), ((j + 1) / ST) & 1);
+          mbar_wait_h(p.wait_hint, k_full(st2), ((j + 1) / ST) & 1);
           tc_fence_after();
           issue_qk(j + 1);
           tc_commit(s_full);
@@ -408,7 +409,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < T; ++j) {
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
-        mbar_wait(kv_empty(st), ph ^ 1);
+        mbar_wait_h(p.wait_hint, kv_empty(st), ph ^ 1);
         mbar_expect_tx(k_full(st), kv_tile);
         for (int c = 0; c < p.dchunks; ++c)
           tma_load_4d(&tmK, k_full(st), k_smem + st * kv_tile + c * A2_KVCHUNK, c * 64, h, j * A2_BKV, b);
@@ -426,7 +427,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int st = j % ST;
         const int n_valid = min(A2_BKV, p.M - j * A2_BKV);
         const uint32_t idesc = make_idesc((n_valid + 15) & ~15, 0, 0);
-        mbar_wait(k_full(st), (j / ST) & 1);
+        mbar_wait_h(p.wait_hint, k_full(st), (j / ST) & 1);
         tc_fence_after();
         const uint32_t kb = k_smem + st * kv_tile;
         const uint32_t sd = tmem_base + (uint32_t)(j & 1) * 64u;
@@ -437,15 +438,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         tc_commit(s_full(j & 1));
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_h(p.wait_hint, q_full, 0);
       tc_fence_after();
       issue_qk(0);
       if (T > 1) issue_qk(1);
       for (int j = 0; j < T; ++j) {
         const int st = j % ST;
         const int n_valid = min(A2_BKV, p.M - j * A2_BKV);
-        mbar_wait(p_full(j & 1), (j >> 1) & 1);       // P_j written (and S_j fully read)
-        mbar_wait(v_full(st), (j / ST) & 1);
+        mbar_wait_h(p.wait_hint, p_full(j & 1), (j >> 1) & 1);       // P_j written (and S_j fully read)
+        mbar_wait_h(p.wait_hint, v_full(st), (j / ST) & 1);
         tc_fence_after();
         const uint32_t vb = v_smem + st * kv_tile;
         const uint32_t pb = p_smem + (uint32_t)(j & 1) * AT_CHUNK;
@@ -666,6 +667,7 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.scale = 1.f / sqrtf((float)d);
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = (bf16*)o; p.lse = lse;
+  p.wait_hint = tc_wait_hint_ns();
   CUtensorMap tq, tk, tv;
   // SIDLSG_ATTN_FWD_V2=1 selects the 64-key double-buffered kernel.  Measured on B200 (B8 N4096 d40): 0.632 ms vs
   // 0.558 ms for the 128-key kernel - the softmax loop is bound by its own MUFU / TMEM-read / issue work, not by waiting
@@ -728,6 +730,7 @@ struct AttnBwdParams {
   const float* delta;    // [B,H,N] = sum_c O dO
   float* dq_acc;         // [B,N,H*d] fp32, zero-initialised by the caller (written through tmDQ)
   int stage_alias;       // dQ staging aliases the P^T/dS^T tiles (d > 64)
+  unsigned wait_hint;    // ns, helper-warp mbarrier waits
   bf16* dk;
   bf16* dv;
   long lddk, lddv;       // row strides (elements) of dk / dv
@@ -795,7 +798,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       for (int i = 0; i < TQ; ++i) {
         const int st = i % QST;
-        mbar_wait(qdo_empty(st), ((i / QST) & 1) ^ 1);
+        mbar_wait_h(p.wait_hint, qdo_empty(st), ((i / QST) & 1) ^ 1);
         mbar_expect_tx(qdo_full(st), 2 * tile_bytes);
         for (int c = 0; c < p.dchunks; ++c) {
           tma_load_4d(&tmQ, qdo_full(st), q_smem + (st * p.dchunks + c) * AT_CHUNK, c * 64, h, i * AT_BQ, b);
@@ -810,7 +813,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_s = make_idesc(128, 0, 0);
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
       const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
-      mbar_wait(kv_full, 0);
+      mbar_wait_h(p.wait_hint, kv_full, 0);
       auto issue_s = [&](int i) {          // S^T_i = K Q_i^T
         const uint32_t qb = q_smem + (i % QST) * tile_bytes;
         for (int s = 0; s < dsteps; ++s) {
@@ -830,7 +833,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // With a two-deep Q/dO ring the S^T of tile i+1 is issued as soon as the compute warps have READ S^T_i, so
       // their exponentials for tile i+1 overlap the dV/dK/dQ MMAs of tile i.
       const bool early = QST == 2;
-      mbar_wait(qdo_full(0), 0);
+      mbar_wait_h(p.wait_hint, qdo_full(0), 0);
       tc_fence_after();
       issue_s(0);
       issue_dp(0);
@@ -838,12 +841,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = i % QST;
         const uint32_t qb = q_smem + st * tile_bytes, dob = do_smem + st * tile_bytes;
         if (early && i + 1 < TQ) {
-          mbar_wait(sread, i & 1);
-          mbar_wait(qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
+          mbar_wait_h(p.wait_hint, sread, i & 1);
+          mbar_wait_h(p.wait_hint, qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
           tc_fence_after();
           issue_s(i + 1);
         }
-        mbar_wait(pds_full, i & 1);
+        mbar_wait_h(p.wait_hint, pds_full, i & 1);
         tc_fence_after();
         for (int s = 0; s < 8; ++s) {      // reduction over the 128 query rows of this tile
           const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
@@ -863,7 +866,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_commit(dq_full);
         if (i + 1 < TQ) {
           if (!early) {
-            mbar_wait(qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
+            mbar_wait_h(p.wait_hint, qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
             tc_fence_after();
             issue_s(i + 1);
           }
@@ -1132,6 +1135,7 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddk = lddk; p.lddv = lddv;
   p.stage_alias = d > 64;
+  p.wait_hint = tc_wait_hint_ns();
   CUtensorMap tq, tk, tv, tdo, tdq;
   if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
       !make_head_map(&tv, v, d, H, M, B, ldv) || !make_head_map(&tdo, dout, d, H, N, B, (long)H * d))

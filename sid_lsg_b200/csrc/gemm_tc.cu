@@ -601,6 +601,11 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
 static int g_tc_state = -1;   // -1 unknown, 0 off, 1 on
 static int g_num_sms = 148;
 int tc_num_sms() { return g_num_sms; }
+unsigned tc_wait_hint_ns() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SIDLSG_WAIT_HINT_NS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  return (unsigned)v;
+}
 
 bool tc_enabled() {
   if (g_tc_state < 0) {

@@ -29,6 +29,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   printf("sidlsg: mbarrier wait timed out (block %d,%d thread %d bar %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar);
   __trap();
 }
+// same, with a suspend-time hint (ns): the polling thread is parked by the hardware for up to `hint_ns` per try instead
+// of re-issuing try_wait + branch every ~40 cycles (half of all warp samples of the attention kernels were such polls,
+// competing for issue slots with the softmax warps of the same scheduler); hint_ns = 0 = plain polling
+__device__ __forceinline__ void mbar_wait_h(uint32_t hint_ns, uint32_t bar, uint32_t parity) {
+  if (hint_ns == 0) { mbar_wait(bar, parity); return; }
+  uint32_t ok = 0;
+  for (long it = 0; it < (1L << 24); ++it) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    if (ok) return;
+  }
+  printf("sidlsg: mbarrier wait timed out (block %d,%d thread %d bar %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar);
+  __trap();
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -163,5 +178,7 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
               const uint32_t* box, const uint32_t* elem_strides = nullptr, int f32 = 0);
 bool tc_enabled();
 int tc_num_sms();
+// SIDLSG_WAIT_HINT_NS (default 0): suspend-time hint of the mbarrier waits of the TMA / MMA helper warps
+unsigned tc_wait_hint_ns();
 
 }  // namespace sidlsg
