@@ -30,6 +30,7 @@ struct AttnParams {
   bf16* o;
   float* lse;
   unsigned wait_hint;    // ns, helper-warp mbarrier waits (tc_wait_hint_ns)
+  long long* trace;      // debug: clock64 stamps of CTA (1,0,0) [tile][16] (sidlsg_attention_trace), else null
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -146,7 +147,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
         const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+        const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
+        if (tr) p.trace[j * 16 + 8] = clock64();
         mbar_wait_h(p.wait_hint, p_full, j & 1);
+        if (tr) p.trace[j * 16 + 9] = clock64();
         mbar_wait_h(p.wait_hint, v_full(st), ph);
         tc_fence_after();
         const uint32_t vb = v_smem + st * tile_bytes;
@@ -157,6 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tc_commit(kv_empty(st));
         tc_commit(o_full);
+        if (tr) p.trace[j * 16 + 10] = clock64();
         if (j + 1 < T) {
           const int st2 = (j + 1) % ST;
           mbar_wait_h(p.wait_hint, k_full(st2), ((j + 1) / ST) & 1);
@@ -164,6 +169,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           issue_qk(j + 1);
           tc_commit(s_full);
         }
+        if (tr) p.trace[j * 16 + 11] = clock64();
       }
     }
   } else {
@@ -273,8 +279,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < T; ++j) {
       const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
       const bool spec = j > 0 && n_valid == AT_BKV;
+      const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32 && threadIdx.x == 0;
+      if (tr) p.trace[j * 16 + 0] = clock64();
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      if (tr) p.trace[j * 16 + 1] = clock64();
       if (!spec) {
         const float m_new = fmaxf(m_used, tile_max(n_valid));
         const bool need = (m_new - m_used) * c > 8.f;
@@ -292,8 +301,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
+      if (tr) p.trace[j * 16 + 2] = clock64();
       float mx = -INFINITY;
       float l_tile = tile_exp(n_valid, m_used, mx);
+      if (tr) p.trace[j * 16 + 3] = clock64();
       if (spec) {
         const float m_new = fmaxf(m_used, mx);
         const bool need = (m_new - m_used) * c > 8.f;
@@ -308,8 +319,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l_run += l_tile;
       tc_fence_before();
       fence_proxy_async();
+      if (tr) p.trace[j * 16 + 4] = clock64();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tr) p.trace[j * 16 + 5] = clock64();
     }
     mbar_wait(o_full, (T - 1) & 1);
     tc_fence_after();
@@ -638,10 +651,16 @@ static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int le
 }
 
 static bool g_attn_attr_done = false;
+static long long* g_attn_trace = nullptr;
 
 }  // namespace sidlsg
 
 using namespace sidlsg;
+
+// debug: device buffer of 32 x 16 int64 that the next attention_fwd launches fill with clock64() stamps of CTA (1,0,0):
+// [tile][0..5] softmax warp 0 (wait S begin / end, O ready, exp done, fenced, arrived), [tile][8..11] MMA warp (wait P
+// begin / end, PV issued, next QK issued).  null = off.  scripts/attn_trace.py prints the phase durations.
+extern "C" int sidlsg_attention_trace(void* buf) { g_attn_trace = (long long*)buf; return SIDLSG_OK; }
 
 // q [B,N,H*d], k/v [B,M,H*d] bf16 with row strides ldq/ldk/ldv elements (batch stride = rows * ld; multiples of 8);
 // o [B,N,H*d] bf16 dense; lse [B,H,N] fp32 (natural log, may be null).
@@ -668,6 +687,7 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = (bf16*)o; p.lse = lse;
   p.wait_hint = tc_wait_hint_ns();
+  p.trace = g_attn_trace;
   CUtensorMap tq, tk, tv;
   // SIDLSG_ATTN_FWD_V2=1 selects the 64-key double-buffered kernel.  Measured on B200 (B8 N4096 d40): 0.632 ms vs
   // 0.558 ms for the 128-key kernel - the softmax loop is bound by its own MUFU / TMEM-read / issue work, not by waiting

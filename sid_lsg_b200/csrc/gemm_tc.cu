@@ -603,7 +603,7 @@ static int g_num_sms = 148;
 int tc_num_sms() { return g_num_sms; }
 unsigned tc_wait_hint_ns() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("SIDLSG_WAIT_HINT_NS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  if (v < 0) { const char* e = getenv("SIDLSG_WAIT_HINT_NS"); v = e ? atoi(e) : 100; if (v < 0) v = 0; }
   return (unsigned)v;
 }
 

@@ -178,7 +178,7 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
               const uint32_t* box, const uint32_t* elem_strides = nullptr, int f32 = 0);
 bool tc_enabled();
 int tc_num_sms();
-// SIDLSG_WAIT_HINT_NS (default 0): suspend-time hint of the mbarrier waits of the TMA / MMA helper warps
+// SIDLSG_WAIT_HINT_NS (default 100; 0 = plain polling): suspend-time hint of the mbarrier waits of the TMA / MMA helper warps
 unsigned tc_wait_hint_ns();
 
 }  // namespace sidlsg
