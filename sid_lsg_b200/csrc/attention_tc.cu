@@ -67,7 +67,12 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
-template <int TCOLS>
+// PT = P stays in TMEM (columns 192..255, d <= 64): the softmax warps write bf16 P with tcgen05.st and the P V MMAs read
+// their A operand from TMEM.  The phase trace (scripts/attn_trace.py) showed the MMA warp needing ~1000 cycles to get
+// 8 P V MMAs + commits through the tensor pipe and ~900 for 3 Q K^T MMAs: with P in shared memory every 128x48x16 MMA
+// fetches 4 KB of A for 24 cycles of math, and the pipe (shared by the two CTAs of the SM) was ~83 % occupied by
+// operand fetch while its math units were 17 % busy.  It also removes the P st.shared + fence.proxy.async (~260 cycles).
+template <int TCOLS, bool PT>
 __global__ void __launch_bounds__(AT_THREADS, TCOLS == 256 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -104,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 128;
+  const uint32_t pt_tmem = tmem_base + 192;          // PT: bf16 P, 64 columns (needs dpad <= 64)
   const uint32_t tile_bytes = p.dchunks * AT_CHUNK;
 
   if (warp == 4) {
@@ -156,8 +162,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t vb = v_smem + st * tile_bytes;
         const int ksteps = (n_valid + 15) >> 4;
         for (int s = 0; s < ksteps; ++s) {
-          tc_mma_bf16(o_tmem, make_desc(p_smem + (s >> 2) * AT_CHUNK + (s & 3) * 32, 1024, 0),
-                      make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, (j > 0 || s > 0) ? 1u : 0u);
+          if (PT)
+            tc_mma_bf16_ta(o_tmem, pt_tmem + s * 8, make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv,
+                           (j > 0 || s > 0) ? 1u : 0u);
+          else
+            tc_mma_bf16(o_tmem, make_desc(p_smem + (s >> 2) * AT_CHUNK + (s & 3) * 32, 1024, 0),
+                        make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, (j > 0 || s > 0) ? 1u : 0u);
         }
         tc_commit(kv_empty(st));
         tc_commit(o_full);
@@ -229,11 +239,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ls2 = fadd2(ls2, pack2(p0, p1));
             pk[i >> 1] = pack_bf16(p0, p1);
           }
+          if (PT) {
+            tmem_st16(pt_tmem + lane_off + (cc >> 1), pk);
+          } else {
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const int u = ((cc & 63) >> 3) + qd;
-            st_shared_v4(p_row + (cc >> 6) * AT_CHUNK + ((u ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
-                         pk[4 * qd + 3]);
+            for (int qd = 0; qd < 4; ++qd) {
+              const int u = ((cc & 63) >> 3) + qd;
+              st_shared_v4(p_row + (cc >> 6) * AT_CHUNK + ((u ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                           pk[4 * qd + 3]);
+            }
           }
         }
         float a0, a1;
@@ -255,12 +269,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ls += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
+          if (PT) {
+            tmem_st16(pt_tmem + lane_off + (cc >> 1), pk);
+          } else {
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            st_shared_v4(p_smem + sw128_offset(row, cc + 8 * qd, AT_CHUNK), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
-                         pk[4 * qd + 3]);
+            for (int qd = 0; qd < 4; ++qd)
+              st_shared_v4(p_smem + sw128_offset(row, cc + 8 * qd, AT_CHUNK), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2],
+                           pk[4 * qd + 3]);
+          }
         }
       }
+      if (PT) tmem_wait_st();
       return ls;
     };
     // O *= f (per-lane factor) in TMEM; all 32 lanes call it together
@@ -318,7 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       l_run += l_tile;
       tc_fence_before();
-      fence_proxy_async();
+      if (!PT) fence_proxy_async();
       if (tr) p.trace[j * 16 + 4] = clock64();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -715,13 +734,17 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
     return SIDLSG_ERR_CUDA;
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
   if (!g_attn_attr_done) {
-    cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_attr_done = true;
   }
+  static int p_tmem = -1;   // SIDLSG_ATTN_PTMEM=0: P through shared memory for every head size (A/B switch)
+  if (p_tmem < 0) { const char* e = getenv("SIDLSG_ATTN_PTMEM"); p_tmem = (e && e[0] == '0') ? 0 : 1; }
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
-  if (p.dpad <= 128) attn_fwd_kernel<256><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  if (p.dpad <= 64 && p_tmem) attn_fwd_kernel<256, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  else if (p.dpad <= 128) attn_fwd_kernel<256, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  else attn_fwd_kernel<512, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   return check_launch("attention_fwd");
 }
 
