@@ -110,6 +110,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 128;
   const uint32_t pt_tmem = tmem_base + 192;          // PT: bf16 P, 64 columns (needs dpad <= 64)
+  // Two O accumulators (even / odd k-steps of P V; columns 128.. and 192..) when they fit: consecutive MMAs into the
+  // SAME accumulator cost ~130 cycles each whatever their size (read-modify-write latency of the TMEM tile - the phase
+  // trace shows ~1000 cycles for the 8 dependent 128x48x16 steps of one P V), independent ones pipeline.
+  const bool two_acc = !PT && TCOLS == 256 && p.dpad <= 64 && p.M >= 32;
+  const uint32_t o2_tmem = tmem_base + 192;
   const uint32_t tile_bytes = p.dchunks * AT_CHUNK;
 
   if (warp == 4) {
@@ -158,27 +163,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait_h(p.wait_hint, p_full, j & 1);
         if (tr) p.trace[j * 16 + 9] = clock64();
         mbar_wait_h(p.wait_hint, v_full(st), ph);
+        const bool more = j + 1 < T;
+        const int st2 = (j + 1) % ST;
+        // with a single K/V stage (d > 128) K_{j+1} can only be loaded after P_j V_j has retired: no interleaving there
+        const bool inter = more && ST >= 2;
+        if (inter) mbar_wait_h(p.wait_hint, k_full(st2), ((j + 1) / ST) & 1);
         tc_fence_after();
         const uint32_t vb = v_smem + st * tile_bytes;
+        const uint32_t kb2 = k_smem + st2 * tile_bytes;
         const int ksteps = (n_valid + 15) >> 4;
-        for (int s = 0; s < ksteps; ++s) {
-          if (PT)
-            tc_mma_bf16_ta(o_tmem, pt_tmem + s * 8, make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv,
-                           (j > 0 || s > 0) ? 1u : 0u);
-          else
-            tc_mma_bf16(o_tmem, make_desc(p_smem + (s >> 2) * AT_CHUNK + (s & 3) * 32, 1024, 0),
-                        make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, (j > 0 || s > 0) ? 1u : 0u);
+        const int n_valid2 = more ? min(AT_BKV, p.M - (j + 1) * AT_BKV) : 0;
+        const uint32_t idesc_s = make_idesc((n_valid2 + 15) & ~15, 0, 0);
+        const int qsteps = inter ? dsteps : 0;
+        // O += P_j V_j and S = Q K_{j+1}^T are independent (S_j was consumed before P_j was published): their k-steps are
+        // issued interleaved so that neighbouring MMAs never wait for each other's accumulator
+        for (int s = 0; s < max(ksteps, qsteps); ++s) {
+          if (s < ksteps) {
+            const uint32_t acc_t = (two_acc && (s & 1)) ? o2_tmem : o_tmem;
+            const uint32_t first = two_acc ? (j == 0 && s < 2) : (j == 0 && s == 0);
+            if (PT)
+              tc_mma_bf16_ta(acc_t, pt_tmem + s * 8, make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, first ? 0u : 1u);
+            else
+              tc_mma_bf16(acc_t, make_desc(p_smem + (s >> 2) * AT_CHUNK + (s & 3) * 32, 1024, 0),
+                          make_desc(vb + s * 2048, 1024, AT_CHUNK), idesc_pv, first ? 0u : 1u);
+          }
+          if (s < qsteps) {
+            const uint32_t off = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+            tc_mma_bf16(s_tmem, make_desc(q_smem + off, 1024, 0), make_desc(kb2 + off, 1024, 0), idesc_s, s > 0);
+          }
         }
         tc_commit(kv_empty(st));
         tc_commit(o_full);
         if (tr) p.trace[j * 16 + 10] = clock64();
-        if (j + 1 < T) {
-          const int st2 = (j + 1) % ST;
+        if (more && !inter) {
           mbar_wait_h(p.wait_hint, k_full(st2), ((j + 1) / ST) & 1);
           tc_fence_after();
           issue_qk(j + 1);
-          tc_commit(s_full);
         }
+        if (more) tc_commit(s_full);
         if (tr) p.trace[j * 16 + 11] = clock64();
       }
     }
@@ -284,13 +306,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     // O *= f (per-lane factor) in TMEM; all 32 lanes call it together
     auto rescale_o = [&](float f) {
-      for (int cc = 0; cc < p.dpad; cc += 16) {
-        uint32_t r[16];
-        tmem_ld16_nowait(o_tmem + lane_off + cc, r);
-        tmem_wait_ld();
+      for (int which = 0; which < (two_acc ? 2 : 1); ++which) {
+        const uint32_t ot = which ? o2_tmem : o_tmem;
+        for (int cc = 0; cc < p.dpad; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16_nowait(ot + lane_off + cc, r);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-        tmem_st16(o_tmem + lane_off + cc, r);
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st16(ot + lane_off + cc, r);
+        }
       }
       tmem_wait_st();
     };
@@ -353,6 +378,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[16];
       tmem_ld16_nowait(o_tmem + lane_off + cc, r);
       tmem_wait_ld();
+      if (two_acc) {
+        uint32_t r2[16];
+        tmem_ld16_nowait(o2_tmem + lane_off + cc, r2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+      }
       if (q < p.N) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -739,8 +771,10 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
     cudaFuncSetAttribute(attn_fwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_attr_done = true;
   }
-  static int p_tmem = -1;   // SIDLSG_ATTN_PTMEM=0: P through shared memory for every head size (A/B switch)
-  if (p_tmem < 0) { const char* e = getenv("SIDLSG_ATTN_PTMEM"); p_tmem = (e && e[0] == '0') ? 0 : 1; }
+  // SIDLSG_ATTN_PTMEM=1: P in TMEM (tested A/B variant; measured 10 % slower than P in shared memory with two
+  // O accumulators, because the P V steps are bound by accumulator latency, not by operand fetch)
+  static int p_tmem = -1;
+  if (p_tmem < 0) { const char* e = getenv("SIDLSG_ATTN_PTMEM"); p_tmem = (e && e[0] == '1') ? 1 : 0; }
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
   if (p.dpad <= 64 && p_tmem) attn_fwd_kernel<256, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   else if (p.dpad <= 128) attn_fwd_kernel<256, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
