@@ -31,6 +31,7 @@ struct AttnParams {
   float* lse;
   unsigned wait_hint;    // ns, helper-warp mbarrier waits (tc_wait_hint_ns)
   long long* trace;      // debug: clock64 stamps of CTA (1,0,0) [tile][16] (sidlsg_attention_trace), else null
+  int interleave;        // SIDLSG_ATTN_INTERLEAVE=1: interleaved P V / Q K^T issue + two O accumulators (A/B variant)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -113,7 +114,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // Two O accumulators (even / odd k-steps of P V; columns 128.. and 192..) when they fit: consecutive MMAs into the
   // SAME accumulator cost ~130 cycles each whatever their size (read-modify-write latency of the TMEM tile - the phase
   // trace shows ~1000 cycles for the 8 dependent 128x48x16 steps of one P V), independent ones pipeline.
-  const bool two_acc = !PT && TCOLS == 256 && p.dpad <= 64 && p.M >= 32;
+  // MEASURED (B8 N4096 d40): 0.634 ms vs 0.549 ms for the plain order - issuing 11 MMAs costs ~2050 cycles either way
+  // (99 per 128x48x16 step, ~220 per 128x128x16 step, 2 CTAs sharing the pipe), so the accumulator-latency theory is
+  // wrong too; kept as an opt-in variant (p.interleave).
+  const bool two_acc = p.interleave && !PT && TCOLS == 256 && p.dpad <= 64 && p.M >= 32;
   const uint32_t o2_tmem = tmem_base + 192;
   const uint32_t tile_bytes = p.dchunks * AT_CHUNK;
 
@@ -166,7 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool more = j + 1 < T;
         const int st2 = (j + 1) % ST;
         // with a single K/V stage (d > 128) K_{j+1} can only be loaded after P_j V_j has retired: no interleaving there
-        const bool inter = more && ST >= 2;
+        const bool inter = p.interleave && more && ST >= 2;
         if (inter) mbar_wait_h(p.wait_hint, k_full(st2), ((j + 1) / ST) & 1);
         tc_fence_after();
         const uint32_t vb = v_smem + st * tile_bytes;
@@ -739,6 +743,11 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.o = (bf16*)o; p.lse = lse;
   p.wait_hint = tc_wait_hint_ns();
   p.trace = g_attn_trace;
+  {
+    static int il = -1;
+    if (il < 0) { const char* e = getenv("SIDLSG_ATTN_INTERLEAVE"); il = (e && e[0] == '1') ? 1 : 0; }
+    p.interleave = il;
+  }
   CUtensorMap tq, tk, tv;
   // SIDLSG_ATTN_FWD_V2=1 selects the 64-key double-buffered kernel.  Measured on B200 (B8 N4096 d40): 0.632 ms vs
   // 0.558 ms for the 128-key kernel - the softmax loop is bound by its own MUFU / TMEM-read / issue work, not by waiting
