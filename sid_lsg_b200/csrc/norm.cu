@@ -3,6 +3,7 @@
 // GroupNorm semantics: diffusers ResnetBlock2D norm1/norm2 + SiLU, Transformer2DModel.norm (eps 1e-6),
 // conv_norm_out.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace sidlsg {
 
@@ -42,7 +43,9 @@ static GnGeom gn_geom(int B, int HW, int C, int V) {
   g.ry = GN_THREADS / g.vx;
   if (g.ry < 1) g.ry = 1;
   if (g.ry > HW) g.ry = HW;
-  int want = (4 * 148 + B - 1) / B;                 // ~4 waves of CTAs
+  static int waves = -1;                            // SIDLSG_GN_WAVES (default 4): CTAs per SM the grid aims at
+  if (waves < 0) { const char* e = getenv("SIDLSG_GN_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
+  int want = (waves * 148 + B - 1) / B;
   int maxc = HW / (g.ry * 2);                       // at least 2 rows per thread
   if (maxc < 1) maxc = 1;
   g.chunks = want < maxc ? want : maxc;
