@@ -103,10 +103,6 @@ int sidlsg_softmax_bwd(const void* P, const float* dP, void* dS, long rows, int 
  * lse [B,H,N] fp32 = log-sum-exp of the scaled scores (kept for the backward; may be null).  d % 8 == 0,
  * 16 <= d <= 192.  Returns SIDLSG_ERR_UNSUPPORTED if the device / shape cannot take the tensor-core path.
  * ref: the attention call of every BasicTransformerBlock.attn1/attn2 (xformers / SDPA in the reference). */
-/* Debug aid (no reference counterpart): device buffer of 32 x 16 int64 filled with clock64() stamps of one CTA by the
-   following sidlsg_attention_fwd launches (phase timeline of the softmax and MMA warps); NULL switches it off. */
-int sidlsg_attention_trace(void* buf);
-
 int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
                          int M, int H, int d, long ldq, long ldk, long ldv, void* stream);
 

@@ -13,7 +13,6 @@ benchq) timeout 1500 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/s
 benchmb) timeout 900 python bench.py --no-cpu-baseline --steps 3 --batch-gpu ${MB:-32} --shapes $OUT/shapes_mb.txt > $OUT/bench_mb.json 2> $OUT/bench_mb.err; tail -c 800 $OUT/bench_mb.err; python scripts/bench_brief.py $OUT/bench_mb.json;;
 benchkb) SIDLSG_BM2_MINKB=${MINKB:-8} timeout 900 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/shapes_kb.txt > $OUT/bench_kb.json 2> $OUT/bench_kb.err; tail -c 800 $OUT/bench_kb.err; python scripts/bench_brief.py $OUT/bench_kb.json;;
 hint) for h in 0 100 400 2000; do echo "== SIDLSG_WAIT_HINT_NS=$h"; SIDLSG_WAIT_HINT_NS=$h timeout 300 python scripts/micro.py attn 10 2>&1 | tee -a $OUT/hint_$h.txt; done;;
-trace) timeout 300 python scripts/attn_trace.py > $OUT/attn_trace.txt 2>&1; cat $OUT/attn_trace.txt;;
 gnw) for w in 4 8 12; do echo "== SIDLSG_GN_WAVES=$w"; SIDLSG_GN_WAVES=$w timeout 300 python scripts/micro.py gn 10 2>&1 | tee -a $OUT/gnw_$w.txt; done;;
 ubench) timeout 120 ./sid_lsg_b200/_C/ubench > $OUT/ubench.txt 2>&1; cat $OUT/ubench.txt;;
 list) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
