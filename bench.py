@@ -326,7 +326,8 @@ def main():
                             "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                             "launches": n, "avg_launch_ms": round(ms / max(n, 1), 4),
                             "algorithmic_flop_per_launch": work / max(n, 1), "share_of_step": round(ms / ms_step, 4),
-                            "measured_on": "1 instrumented step right after the timed region (per-call CUDA events on the launch stream)"}
+                            "measured_on": "1 instrumented step right after the timed region (per-call CUDA events on the launch stream)",
+                            "limiter": "L2->SM operand delivery, 42-47 B/clk/SM in ncu (l1tex__m_xbar2l1tex_read_bytes; profiles/r01_ncu_conv_*.txt): 256-row tiles cut bytes per FLOP 1.4-1.5x; the FLOP roofline is reported because the contract offers hbm|tensor"}
         line["kernels"] = kern
         if args.shapes:
             with open(args.shapes, "w") as f:
