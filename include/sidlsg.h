@@ -34,6 +34,12 @@ extern "C" {
 const char* sidlsg_last_error();
 int sidlsg_version();
 int sidlsg_device_arch(int device);
+/* Host-only diagnostic (runs without a GPU): the tile shape the tcgen05 GEMM / implicit-GEMM path chooses for a problem.
+   kind 0 linear fwd, 1 linear dgrad, 2 linear wgrad (split-K), 3 conv3x3 fwd, 4 conv3x3 dgrad (M = pixels, N = output
+   channels, K = input channels), 5 conv3x3 wgrad (M = Cout, N = Cin, K = pixels).
+   out[8] = {256-row tiles?, block_n, m_tiles, n_tiles, splits, smem ring stages, stage bytes, 64-deep k-blocks}. */
+int sidlsg_debug_tiling(int kind, long M, int N, long K, int* out);
+
 /* diagnostics: out (HOST memory) long[2] = {tcgen05 GEMM/conv launches, CUDA-core GEMM/conv launches} */
 int sidlsg_counters(long* out);
 /* 1 if the calling thread's last sidlsg_gemm / sidlsg_conv3x3 / sidlsg_conv3x3_wgrad ran on tcgen05, else 0 */

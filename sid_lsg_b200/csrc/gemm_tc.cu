@@ -786,21 +786,23 @@ static bool make_out_map(CUtensorMap* m, TcParams& p, void* c, long M, long N, l
   return true;
 }
 
+// narrow tiles leave room for a deeper ring: K = 320 GEMMs (5 k-blocks per tile) then prefetch more than one whole tile
+// ahead while the epilogue of the previous tile drains
+static void plan_stages(TcParams& p) {
+  const bool b_mn = p.b_mode != B_K2D;
+  const int b_bytes = b_mn ? ((p.block_n + 63) >> 6) * 8192 : p.block_n * 128;
+  p.stage_bytes = (p.bm2 ? 2 : 1) * TC_A_BYTES + b_bytes;
+  int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;     // what fits in the 192 KB ring
+  p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < 2 ? 2 : ns);
+}
+
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, TcParams& p, cudaStream_t st) {
   long tiles = (long)p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
   if (tiles <= 0) return SIDLSG_OK;
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
   g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  {
-    // narrow tiles leave room for a deeper ring: K = 320 GEMMs (5 k-blocks per tile) then prefetch more than one
-    // whole tile ahead while the epilogue of the previous tile drains
-    const bool b_mn = p.b_mode != B_K2D;
-    const int b_bytes = b_mn ? ((p.block_n + 63) >> 6) * 8192 : p.block_n * 128;
-    p.stage_bytes = (p.bm2 ? 2 : 1) * TC_A_BYTES + b_bytes;
-    int ns = TC_STAGES * TC_STAGE_BYTES / p.stage_bytes;     // what fits in the 192 KB ring
-    p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < 2 ? 2 : ns);
-  }
+  plan_stages(p);
   if (p.bm2) gemm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   else gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
@@ -814,6 +816,35 @@ static int pick_splits(long tiles, int kb_total) {
   if (s < 1) s = 1;
   if (s > 128) s = 128;
   return (int)s;
+}
+
+// tile shape / split count of a dense GEMM (everything but pointers): shared by tc_gemm_try and sidlsg_debug_tiling
+static void plan_dense(TcParams& p, int M, int N, int K, bool a_k, bool b_mn, int accumulate, int nbatch, int out_dtype) {
+  p.m_tiles = (M + TC_BM - 1) / TC_BM;
+  p.block_n = pick_block_n(N, b_mn);
+  if (accumulate == 0 && nbatch == 1) {
+    const int kbt = (K + TC_BK - 1) / TC_BK;
+    const GridTiling t1 = pick_block_n_grid(N, b_mn, p.m_tiles, kbt);
+    p.block_n = t1.bn;
+    // 256-row tiles for the L2-bound (deep-K) GEMMs with enough rows to keep every SM busy
+    const int mode = bm2_mode();
+    static int min_kb = -1;   // SIDLSG_BM2_MINKB: shallowest reduction (in 64-element blocks) that gets 256-row tiles
+    if (min_kb < 0) { const char* e = getenv("SIDLSG_BM2_MINKB"); min_kb = e ? atoi(e) : 16; if (min_kb < 1) min_kb = 1; }
+    if (mode && a_k && out_dtype == SIDLSG_BF16 && ((kbt >= min_kb && M >= 512) || (mode == 2 && M >= 256))) {
+      const long mt2 = (M + 2 * TC_BM - 1) / (2 * TC_BM);
+      const GridTiling t2 = pick_block_n_grid(N, b_mn, mt2, kbt, true);
+      if (mode == 2 || t2.cost < t1.cost * 0.95) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
+    }
+  }
+  p.kb_total = (K + TC_BK - 1) / TC_BK;
+  p.splits = 1;
+  if (accumulate == 2 && nbatch == 1 && b_mn) {
+    const SplitTiling tl = pick_split_tiling(N, 1, p.m_tiles, p.kb_total);
+    p.block_n = tl.bn;
+    p.splits = tl.splits;
+  }
+  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  if (accumulate == 2 && !(nbatch == 1 && b_mn)) p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
 }
 
 // Returns 1 if handled on the tensor cores, 0 if the shape is not eligible (caller falls back to the CUDA-core
@@ -843,31 +874,7 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.cstride = 1;
-  p.m_tiles = (M + TC_BM - 1) / TC_BM;
-  p.block_n = pick_block_n(N, b_mn);
-  if (accumulate == 0 && nbatch == 1) {
-    const int kbt = (K + TC_BK - 1) / TC_BK;
-    const GridTiling t1 = pick_block_n_grid(N, b_mn, p.m_tiles, kbt);
-    p.block_n = t1.bn;
-    // 256-row tiles for the L2-bound (deep-K) GEMMs with enough rows to keep every SM busy
-    const int mode = bm2_mode();
-    static int min_kb = -1;   // SIDLSG_BM2_MINKB: shallowest reduction (in 64-element blocks) that gets 256-row tiles
-    if (min_kb < 0) { const char* e = getenv("SIDLSG_BM2_MINKB"); min_kb = e ? atoi(e) : 16; if (min_kb < 1) min_kb = 1; }
-    if (mode && a_k && out_dtype == SIDLSG_BF16 && ((kbt >= min_kb && M >= 512) || (mode == 2 && M >= 256))) {
-      const long mt2 = (M + 2 * TC_BM - 1) / (2 * TC_BM);
-      const GridTiling t2 = pick_block_n_grid(N, b_mn, mt2, kbt, true);
-      if (mode == 2 || t2.cost < t1.cost * 0.95) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
-    }
-  }
-  p.kb_total = (K + TC_BK - 1) / TC_BK;
-  p.splits = 1;
-  if (accumulate == 2 && nbatch == 1 && b_mn) {
-    const SplitTiling tl = pick_split_tiling(N, 1, p.m_tiles, p.kb_total);
-    p.block_n = tl.bn;
-    p.splits = tl.splits;
-  }
-  p.n_tiles = (N + p.block_n - 1) / p.block_n;
-  if (accumulate == 2 && !(nbatch == 1 && b_mn)) p.splits = pick_splits((long)p.m_tiles * p.n_tiles, p.kb_total);
+  plan_dense(p, M, N, K, a_k, b_mn, accumulate, nbatch, out_dtype);
   p.a_mode = a_k ? A_K2D : A_MN2D;
   p.b_mode = b_k ? B_K2D : B_MN2D;
   p.c = c; p.ldc = ldc; p.out_f32 = out_dtype == SIDLSG_F32;
@@ -890,6 +897,20 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
   if (!make_out_map(&tcm, p, c, M, N, ldc)) return SIDLSG_ERR_CUDA;
   int r = launch_tc(ta, tb, tcm, p, st);
   return r == SIDLSG_OK ? 1 : r;
+}
+
+// tile shape of the implicit-GEMM convolution (forward / data gradient)
+static void plan_conv(TcParams& p, long M, int N, int Kc, bool dgrad) {
+  p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  const int kbt = 9 * (Kc / 64);
+  const GridTiling t1 = pick_block_n_grid(N, dgrad, p.m_tiles, kbt);
+  p.block_n = t1.bn;
+  const int mode = bm2_mode();
+  if (mode && M >= 256 && (M % (2 * TC_BM)) == 0) {
+    const long mt2 = M / (2 * TC_BM);
+    const GridTiling t2 = pick_block_n_grid(N, dgrad, mt2, kbt, true);
+    if (mode == 2 || (M >= 512 && t2.cost < t1.cost * 0.95)) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
+  }
 }
 
 // tile geometry for cutting 128 (or 64) consecutive pixels out of [B, H, W, C]: whole image rows only
@@ -927,18 +948,7 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = N;
-  p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
-  {
-    const int kbt = 9 * (Kc / 64);
-    const GridTiling t1 = pick_block_n_grid(N, dgrad, p.m_tiles, kbt);
-    p.block_n = t1.bn;
-    const int mode = bm2_mode();
-    if (mode && M >= 256 && (M % (2 * TC_BM)) == 0) {
-      const long mt2 = M / (2 * TC_BM);
-      const GridTiling t2 = pick_block_n_grid(N, dgrad, mt2, kbt, true);
-      if (mode == 2 || (M >= 512 && t2.cost < t1.cost * 0.95)) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
-    }
-  }
+  plan_conv(p, M, N, Kc, dgrad);
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.splits = 1;
   p.cchunks = Kc / 64;
@@ -1023,6 +1033,44 @@ int tc_conv3x3_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
 }
 
 }  // namespace sidlsg
+
+// Host-only diagnostic (no GPU needed): the tiling the tensor-core path would choose.
+//   kind 0 linear fwd (A, B K-major), 1 linear dgrad (B MN-major), 2 linear wgrad (A, B MN-major, split-K),
+//   3 conv3x3 fwd, 4 conv3x3 dgrad (M = pixels, N = output channels, K = input channels), 5 conv3x3 wgrad (M = Cout,
+//   N = Cin, K = pixels).  out[8] = {bm2, block_n, m_tiles, n_tiles, splits, stages, stage_bytes, kb_total}.
+extern "C" int sidlsg_debug_tiling(int kind, long M, int N, long K, int* out) {
+  using namespace sidlsg;
+  if (kind < 0 || kind > 5 || M <= 0 || N <= 0 || K <= 0) { set_error("sidlsg_debug_tiling: bad arguments"); return SIDLSG_ERR_ARG; }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N;
+  if (kind <= 2) {
+    const bool a_k = kind != 2, b_mn = kind != 0;
+    plan_dense(p, (int)M, N, (int)K, a_k, b_mn, kind == 2 ? 2 : 0, 1, kind == 2 ? SIDLSG_F32 : SIDLSG_BF16);
+    p.a_mode = a_k ? A_K2D : A_MN2D;
+    p.b_mode = b_mn ? B_MN2D : B_K2D;
+  } else if (kind <= 4) {
+    plan_conv(p, M, N, (int)K, kind == 4);
+    p.n_tiles = (N + p.block_n - 1) / p.block_n;
+    p.splits = 1;
+    p.kb_total = 9 * ((int)K / 64);
+    p.a_mode = A_CONV;
+    p.b_mode = kind == 4 ? B_W3D : B_K2D;
+  } else {
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    p.kb_total = (int)(K / 64);
+    const SplitTiling tl = pick_split_tiling(N, 9, p.m_tiles, p.kb_total);
+    p.block_n = tl.bn;
+    p.splits = tl.splits;
+    p.n_tiles = 9 * ((N + p.block_n - 1) / p.block_n);
+    p.a_mode = A_MN2D;
+    p.b_mode = B_CONV;
+  }
+  plan_stages(p);
+  out[0] = p.bm2; out[1] = p.block_n; out[2] = p.m_tiles; out[3] = p.n_tiles; out[4] = p.splits; out[5] = p.stages;
+  out[6] = p.stage_bytes; out[7] = p.kb_total;
+  return SIDLSG_OK;
+}
 
 // diagnostics: out[0] = tcgen05 GEMM/conv launches, out[1] = CUDA-core GEMM/conv launches (host memory)
 extern "C" int sidlsg_last_path() { return sidlsg::g_last_path; }

@@ -190,3 +190,43 @@ def test_iteration_matches_oracle_fp32_and_bf16():
                 num = sum(float(((sd[k].cpu() - init[k]) - (rd[k] - init[k])).pow(2).sum()) for k in rd)
                 den = sum(float((rd[k] - init[k]).pow(2).sum()) for k in rd)
                 assert (num / max(den, 1e-30)) ** 0.5 < 2e-2, (num, den)
+
+
+def test_training_state_roundtrip(tmp_path):
+    """training-state save / load (training/checkpoint.py; reference: sid_training_loop.py:296-310, 654-656): networks,
+    Adam second-moment buckets, step counts and the image counter come back bit-exactly, the bf16 shadow is refreshed."""
+    import sid_lsg_b200 as S
+    from sid_lsg_b200.training import checkpoint as ck
+    from sid_lsg_b200.training.step import synth_microbatch
+    nets = []
+    for i in range(4):
+        _, m, cfg = make_pair("TINY", torch.bfloat16, seed=0)
+        nets.append(m)
+    st = S.SiDLSGStep(nets[0], nets[1], nets[2], nets[3], S.DDPMScheduler(device=DEV), lr=1e-4, glr=1e-4,
+                      cfg_train_fake=1.5, cfg_eval_fake=1.5, cfg_eval_real=1.5)
+    mbf = [synth_microbatch(2, cfg, 21, DEV, dropout=True)]
+    mbg = [synth_microbatch(2, cfg, 22, DEV)]
+    st.iteration(mbf, mbg, batch_size=2)
+    torch.cuda.synchronize()
+    f = ck.save_training_state(st, str(tmp_path / "training-state-000000.pt"))
+    want = {}
+    for name, net in (("fake", st.fake_score), ("G", st.G), ("ema", st.G_ema)):
+        want[name] = net.flat.master.clone()
+    want_v = {"fake": st.fake_score.flat.exp_avg_sq.clone(), "G": st.G.flat.exp_avg_sq.clone()}
+    nimg, steps = st.cur_nimg, st.G.flat.step_count
+    st.iteration(mbf, mbg, batch_size=2)                    # move every piece of state away from the saved one
+    torch.cuda.synchronize()
+    assert not torch.equal(st.G.flat.master, want["G"])
+    ck.load_training_state(st, f)
+    torch.cuda.synchronize()
+    for name, net in (("fake", st.fake_score), ("G", st.G), ("ema", st.G_ema)):
+        assert torch.equal(net.flat.master, want[name]), name
+        assert torch.equal(net.flat.shadow, net.flat.master.to(torch.bfloat16)), name
+    assert torch.equal(st.fake_score.flat.exp_avg_sq, want_v["fake"]) and torch.equal(st.G.flat.exp_avg_sq, want_v["G"])
+    assert st.cur_nimg == nimg and st.G.flat.step_count == steps and st.fake_score.flat.step_count == steps
+    # the optimiser entries are loadable by the reference's torch.optim.Adam (beta1 = 0: zero first moments)
+    data = torch.load(f, map_location="cpu", weights_only=False)
+    ref_params = [torch.nn.Parameter(torch.zeros(p.shape)) for p in st.G.parameters()]
+    opt = torch.optim.Adam(ref_params, lr=1e-4, betas=(0.0, 0.999), eps=1e-8)
+    opt.load_state_dict(data["g_optimizer_state"])
+    assert len(opt.state) == len(ref_params)
