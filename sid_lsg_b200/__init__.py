@@ -7,6 +7,7 @@ from .scheduler import DDPMScheduler  # noqa: F401
 from .params import FlatParams  # noqa: F401
 from .training.sid_sd_util import sid_sd_sampler, sid_sd_denoise, PromptBatch  # noqa: F401
 from .training.step import SiDLSGStep, synth_microbatch, ema_beta  # noqa: F401
+from .training.prompts import PromptEncoder  # noqa: F401
 from .training import checkpoint  # noqa: F401
 from .training.checkpoint import load_unet, save_unet, save_network_snapshot, load_network_snapshot  # noqa: F401
 from .training.checkpoint import save_training_state, load_training_state  # noqa: F401
