@@ -14,6 +14,7 @@ benchmb) timeout 900 python bench.py --no-cpu-baseline --steps 3 --batch-gpu ${M
 benchkb) SIDLSG_BM2_MINKB=${MINKB:-8} timeout 900 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/shapes_kb.txt > $OUT/bench_kb.json 2> $OUT/bench_kb.err; tail -c 800 $OUT/bench_kb.err; python scripts/bench_brief.py $OUT/bench_kb.json;;
 hint) for h in 0 100 400 2000; do echo "== SIDLSG_WAIT_HINT_NS=$h"; SIDLSG_WAIT_HINT_NS=$h timeout 300 python scripts/micro.py attn 10 2>&1 | tee -a $OUT/hint_$h.txt; done;;
 gnw) for w in 4 8 12; do echo "== SIDLSG_GN_WAVES=$w"; SIDLSG_GN_WAVES=$w timeout 300 python scripts/micro.py gn 10 2>&1 | tee -a $OUT/gnw_$w.txt; done;;
+ubench_mma) timeout 120 ./sid_lsg_b200/_C/ubench_mma > $OUT/ubench_mma.txt 2>&1; cat $OUT/ubench_mma.txt;;
 ubench) timeout 120 ./sid_lsg_b200/_C/ubench > $OUT/ubench.txt 2>&1; cat $OUT/ubench.txt;;
 list) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
         python bench.py --batch 16 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-roofline > $OUT/list_bench.log 2>&1
