@@ -66,7 +66,7 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
-template <int TCOLS>
+template <int TCOLS, bool ELECT>
 __global__ void __launch_bounds__(AT_THREADS, TCOLS == 256 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -107,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (role_leader<ELECT>(lane)) {
       mbar_expect_tx(q_full, tile_bytes);
       for (int c = 0; c < p.dchunks; ++c) tma_load_4d(&tmQ, q_full, q_smem + c * AT_CHUNK, c * 64, h, q0, b);
       for (int j = 0; j < T; ++j) {
@@ -124,7 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (role_leader<ELECT>(lane)) {
       const int dsteps = p.dpad >> 4;
       auto issue_qk = [&](int j) {
         const int st = j % ST;
@@ -695,13 +695,20 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
     return SIDLSG_ERR_CUDA;
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
   if (!g_attn_attr_done) {
-    cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_attr_done = true;
   }
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
-  if (p.dpad <= 128) attn_fwd_kernel<256><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  if (tc_elect_enabled()) {
+    if (p.dpad <= 128) attn_fwd_kernel<256, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+    else attn_fwd_kernel<512, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  } else {
+    if (p.dpad <= 128) attn_fwd_kernel<256, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+    else attn_fwd_kernel<512, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  }
   return check_launch("attention_fwd");
 }
 
@@ -736,6 +743,7 @@ struct AttnBwdParams {
   long lddk, lddv;       // row strides (elements) of dk / dv
 };
 
+template <bool ELECT>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -790,7 +798,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (role_leader<ELECT>(lane)) {
       mbar_expect_tx(kv_full, 2 * tile_bytes);
       for (int c = 0; c < p.dchunks; ++c) {
         tma_load_4d(&tmK, kv_full, k_smem + c * AT_CHUNK, c * 64, h, kv0, b);
@@ -808,7 +816,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (role_leader<ELECT>(lane)) {
       const int dsteps = p.dpad >> 4;
       const uint32_t idesc_s = make_idesc(128, 0, 0);
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
@@ -1150,11 +1158,13 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256 +
                    (p.stage_alias ? 0 : ((d + 31) / 32) * AT_CHUNK);
   if (!g_attn_bwd_attr_done) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_bwd_attr_done = true;
   }
   dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
-  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  if (tc_elect_enabled()) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  else attn_bwd_kernel<false><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;
   // dq (bf16) = dq_acc (fp32)

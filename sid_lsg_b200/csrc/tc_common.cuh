@@ -87,6 +87,24 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// One lane of a fully converged warp (elect.sync).  As the CONDITION of the role branch it tells nvcc that exactly one
+// thread is active inside: with `if (lane == 0)` every tcgen05.mma / TMA instruction of the branch is wrapped in an
+// "ELECT ... BRA.U.ANY" loop over the possibly-many active lanes (6 extra instructions and a branch per MMA; the MMA
+// issuer then spends 100-220 cycles per MMA - scripts/ubench_mma.cu measures 184 - and caps the pipe at one 128 x 256
+// x 16 MMA per 184 cycles), with `if (elect_one())` the UTCHMMAs are issued back to back (checked in SASS).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\nselp.u32 %0, 1, 0, e;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// role leader of a single-thread role (TMA producer, MMA issuer): ELECT = the elect.sync form (opt-in until validated on
+// a GPU: SIDLSG_ELECT=1), otherwise lane 0
+template <bool ELECT>
+__device__ __forceinline__ bool role_leader(int lane) {
+  if constexpr (ELECT) return elect_one();
+  else return lane == 0;
+}
+
 // named barrier among `n` threads (ids 1.. ; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -187,5 +205,7 @@ bool tc_enabled();
 int tc_num_sms();
 // SIDLSG_WAIT_HINT_NS (default 100; 0 = plain polling): suspend-time hint of the mbarrier waits of the TMA / MMA helper warps
 unsigned tc_wait_hint_ns();
+// SIDLSG_ELECT=1: kernels instantiated with elect.sync role leaders (see elect_one)
+bool tc_elect_enabled();
 
 }  // namespace sidlsg
