@@ -2,7 +2,9 @@
 // accumulators, the A operand source (shared memory vs TMEM) and the number of CTAs sharing the SM's tensor pipe.
 // Written after the attention phase trace (profiles/r01_attn_fwd_phase_trace.txt) showed the MMA-issuing thread spending
 // ~100 cycles per 128x48x16 step and ~220 per 128x128x16 step: this isolates that cost from everything else.
-// NOT YET RUN (round 1 ended without GPU minutes); operands are uninitialised shared memory - only timing matters.
+// Round-1 result for the lane-0 form: a constant 184 cycles per MMA (profiles/r01_ubench_mma_issue_b200.txt) - the
+// issuing thread's ELECT..BRA.U.ANY loop, not the pipe.  The elect.sync form (second table) has NOT been run yet.
+// Operands are uninitialised shared memory - only timing matters.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Isid_lsg_b200/csrc -Iinclude -o ubench_mma scripts/ubench_mma.cu
 #include "tc_common.cuh"
 
@@ -10,6 +12,7 @@ using namespace sidlsg;
 
 struct MmaCfg { int N, nacc, a_tmem, reps, tcols; };
 
+template <bool ELECT>
 __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCfg c) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -24,7 +27,8 @@ __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCf
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot_ptr;
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+   if (role_leader<ELECT>(lane)) {
     const uint32_t idesc = make_idesc(c.N, 0, 0);
     const uint32_t a_t = tmem + c.nacc * c.N;            // A-in-TMEM region behind the accumulators (32 columns = K 64)
     const long long t0 = clock64();
@@ -44,6 +48,7 @@ __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCf
     const long long t2 = clock64();
     out[blockIdx.x * 2] = t1 - t0;
     out[blockIdx.x * 2 + 1] = t2 - t0;
+   }
   }
   tc_fence_before();
   __syncthreads();
@@ -53,11 +58,10 @@ __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCf
   }
 }
 
-int main() {
-  long long* out;
-  cudaMalloc(&out, 2 * 296 * sizeof(long long));
-  const int smem = 16384 + 32768 + 1024 + 64;
-  cudaFuncSetAttribute(mma_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <bool ELECT>
+static int sweep(long long* out, int smem) {
+  cudaFuncSetAttribute(mma_issue_kernel<ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  printf("---- issuing thread = %s\n", ELECT ? "if (elect_one())  [elect.sync]" : "if (lane == 0)");
   printf("%4s %5s %6s %8s | %10s %12s   (cycles per 128xNx16 MMA; nominal math = N/2)\n", "N", "nacc", "A", "CTAs/SM",
          "issue", "issue+drain");
   for (int ctas = 1; ctas <= 2; ++ctas)
@@ -69,7 +73,7 @@ int main() {
           MmaCfg c{N, nacc, a_tmem, 256, tcols};
           long long h[2 * 296];
           for (int rep = 0; rep < 2; ++rep) {
-            mma_issue_kernel<<<148 * ctas, 128, smem>>>(out, c);
+            mma_issue_kernel<ELECT><<<148 * ctas, 128, smem>>>(out, c);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           }
@@ -80,4 +84,12 @@ int main() {
           printf("%4d %5d %6s %8d | %10.1f %12.1f\n", N, nacc, a_tmem ? "TMEM" : "smem", ctas, iss / n, tot / n);
         }
   return 0;
+}
+
+int main() {
+  long long* out;
+  cudaMalloc(&out, 2 * 296 * sizeof(long long));
+  const int smem = 16384 + 32768 + 1024 + 64;
+  if (sweep<true>(out, smem)) return 1;
+  return sweep<false>(out, smem);
 }
