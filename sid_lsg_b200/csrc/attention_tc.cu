@@ -66,7 +66,7 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
-template <int TCOLS, bool ELECT>
+template <int TCOLS>
 __global__ void __launch_bounds__(AT_THREADS, TCOLS == 256 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -107,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       mbar_expect_tx(q_full, tile_bytes);
       for (int c = 0; c < p.dchunks; ++c) tma_load_4d(&tmQ, q_full, q_smem + c * AT_CHUNK, c * 64, h, q0, b);
       for (int j = 0; j < T; ++j) {
@@ -124,7 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       const int dsteps = p.dpad >> 4;
       auto issue_qk = [&](int j) {
         const int st = j % ST;
@@ -346,288 +346,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Forward, experimental variant (d <= 128, SIDLSG_ATTN_FWD_V2=1): 64-key tiles with TWO score buffers in TMEM, so the
-// MMA warp runs one tile ahead of the softmax warps - S_{j+1} = Q K_{j+1}^T is issued while the exponentials of tile j
-// are still running and the softmax warps never wait for the tensor pipe.  Correct (parity tests) but 13 % SLOWER than
-// the 128-key kernel above on B200, which shows that kernel is not stalled on the MMA round trip.  TMEM: S0 | S1 (64 columns each) | O (<= 128) = 256
-// columns, two CTAs per SM for d <= 64 as before.  P is double buffered in shared memory ([128 x 64] bf16 each).
-//   MMA issue order: QK(0) QK(1) PV(0) QK(2) PV(1) QK(3) ...   (QK(j+2) reuses S[j&1], free once P_j has been written)
-//   barriers: s_full[2] (MMA -> softmax), p_full[2] (softmax -> MMA, 4 warp arrivals), p_free[2] (P_j V_j retired: the
-//   P buffer may be rewritten / O is quiescent), k_full / v_full / kv_empty[ST] (TMA ring), o_done.
-constexpr int A2_BKV = 64;
-constexpr int A2_KVCHUNK = 8192;     // [64 rows][64 bf16] SWIZZLE_128B
-constexpr int A2_MAXST = 4;
-
-template <int UNUSED>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem_base = smem_u32(smem_raw);
-  const int ST = p.kv_stages;
-  const uint32_t kv_tile = p.dchunks * A2_KVCHUNK;
-  const uint32_t q_smem = smem_base;
-  const uint32_t k_smem = q_smem + p.dchunks * AT_CHUNK;
-  const uint32_t v_smem = k_smem + ST * kv_tile;
-  const uint32_t p_smem = v_smem + ST * kv_tile;            // 2 x 16 KB
-  const uint32_t bar_base = p_smem + 2 * AT_CHUNK;
-  const uint32_t q_full = bar_base, o_done = bar_base + 8;
-  auto s_full = [&](int b) { return bar_base + 16 + 8u * b; };
-  auto p_full = [&](int b) { return bar_base + 32 + 8u * b; };
-  auto p_free = [&](int b) { return bar_base + 48 + 8u * b; };
-  auto k_full = [&](int s) { return bar_base + 64 + 8u * s; };
-  auto v_full = [&](int s) { return bar_base + 96 + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 128 + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 160;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
-  const int T = (p.M + A2_BKV - 1) / A2_BKV;
-
-  if (threadIdx.x == 0) {
-    if (smem_base & 1023u) { printf("sidlsg attention: dynamic smem not 1024-aligned\n"); __trap(); }
-    mbar_init(q_full, 1); mbar_init(o_done, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 4); mbar_init(p_free(i), 1); }
-    for (int i = 0; i < A2_MAXST; ++i) { mbar_init(k_full(i), 1); mbar_init(v_full(i), 1); mbar_init(kv_empty(i), 1); }
-    fence_barrier_init();
-  }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t o_tmem = tmem_base + 128;
-
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(q_full, p.dchunks * AT_CHUNK);
-      for (int c = 0; c < p.dchunks; ++c) tma_load_4d(&tmQ, q_full, q_smem + c * AT_CHUNK, c * 64, h, q0, b);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % ST;
-        const uint32_t ph = (j / ST) & 1;
-        mbar_wait_h(p.wait_hint, kv_empty(st), ph ^ 1);
-        mbar_expect_tx(k_full(st), kv_tile);
-        for (int c = 0; c < p.dchunks; ++c)
-          tma_load_4d(&tmK, k_full(st), k_smem + st * kv_tile + c * A2_KVCHUNK, c * 64, h, j * A2_BKV, b);
-        mbar_expect_tx(v_full(st), kv_tile);
-        for (int c = 0; c < p.dchunks; ++c)
-          tma_load_4d(&tmV, v_full(st), v_smem + st * kv_tile + c * A2_KVCHUNK, c * 64, h, j * A2_BKV, b);
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const int dsteps = p.dpad >> 4;
-      const uint32_t idesc_pv = make_idesc(p.dpad, 0, 1);
-      auto issue_qk = [&](int j) {
-        const int st = j % ST;
-        const int n_valid = min(A2_BKV, p.M - j * A2_BKV);
-        const uint32_t idesc = make_idesc((n_valid + 15) & ~15, 0, 0);
-        mbar_wait_h(p.wait_hint, k_full(st), (j / ST) & 1);
-        tc_fence_after();
-        const uint32_t kb = k_smem + st * kv_tile;
-        const uint32_t sd = tmem_base + (uint32_t)(j & 1) * 64u;
-        for (int s2 = 0; s2 < dsteps; ++s2) {
-          const uint32_t qoff = (s2 >> 2) * AT_CHUNK + (s2 & 3) * 32;
-          const uint32_t koff = (s2 >> 2) * A2_KVCHUNK + (s2 & 3) * 32;
-          tc_mma_bf16(sd, make_desc(q_smem + qoff, 1024, 0), make_desc(kb + koff, 1024, 0), idesc, s2 > 0);
-        }
-        tc_commit(s_full(j & 1));
-      };
-      mbar_wait_h(p.wait_hint, q_full, 0);
-      tc_fence_after();
-      issue_qk(0);
-      if (T > 1) issue_qk(1);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % ST;
-        const int n_valid = min(A2_BKV, p.M - j * A2_BKV);
-        mbar_wait_h(p.wait_hint, p_full(j & 1), (j >> 1) & 1);       // P_j written (and S_j fully read)
-        mbar_wait_h(p.wait_hint, v_full(st), (j / ST) & 1);
-        tc_fence_after();
-        const uint32_t vb = v_smem + st * kv_tile;
-        const uint32_t pb = p_smem + (uint32_t)(j & 1) * AT_CHUNK;
-        const int ksteps = (n_valid + 15) >> 4;
-        for (int s2 = 0; s2 < ksteps; ++s2)
-          tc_mma_bf16(o_tmem, make_desc(pb + s2 * 32, 1024, 0), make_desc(vb + s2 * 2048, 1024, A2_KVCHUNK), idesc_pv,
-                      (j > 0 || s2 > 0) ? 1u : 0u);
-        tc_commit(kv_empty(st));                        // K_j (read by the earlier QK(j)) and V_j are free
-        tc_commit(p_free(j & 1));
-        if (j == T - 1) tc_commit(o_done);
-        if (j + 2 < T) issue_qk(j + 2);                 // S[j&1] is free: P_j exists, so S_j has been read
-      }
-    }
-  } else {
-    // ===================== softmax / output (warps 0-3), one query row per thread =====================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const float c = p.scale_log2;
-    const uint64_t c2 = pack2(c, c);
-    const int rx = row & 7;
-    float m_used = -INFINITY, l_run = 0.f;
-
-    auto tile_max = [&](uint32_t s_tmem, int n_valid) {
-      float mx = -INFINITY;
-      for (int cc = 0; cc < n_valid; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32_nowait(s_tmem + lane_off + cc, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (cc + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      return mx;
-    };
-    // P = exp2(s*c - m*c) -> bf16 smem tile `pbuf`; returns the row sum, tracks the raw row max in mx
-    auto tile_exp = [&](uint32_t s_tmem, uint32_t pbuf, int n_valid, float m, float& mx) {
-      const float nmc = -m * c;
-      const uint64_t nmc2 = pack2(nmc, nmc);
-      const uint32_t p_row = pbuf + row * 128;
-      float ls = 0.f;
-      if (n_valid == A2_BKV) {
-        uint64_t ls2 = pack2(0.f, 0.f);
-#pragma unroll
-        for (int cc = 0; cc < A2_BKV; cc += 32) {
-          uint32_t r[32], pk[16];
-          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
-            mx = fmaxf(fmaxf(mx, x0), x1);
-            float t0, t1;
-            unpack2(ffma2(pack2(x0, x1), c2, nmc2), t0, t1);
-            const float p0 = ex2f(t0), p1 = ex2f(t1);
-            ls2 = fadd2(ls2, pack2(p0, p1));
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const int u = (cc >> 3) + qd;
-            st_shared_v4(p_row + ((u ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-          }
-        }
-        float a0, a1;
-        unpack2(ls2, a0, a1);
-        ls = a0 + a1;
-      } else {
-        for (int cc = 0; cc < n_valid; cc += 32) {
-          uint32_t r[32], pk[16];
-          tmem_ld32_nowait(s_tmem + lane_off + cc, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const bool v0 = cc + i < n_valid, v1 = cc + i + 1 < n_valid;
-            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
-            if (v0) mx = fmaxf(mx, x0);
-            if (v1) mx = fmaxf(mx, x1);
-            const float p0 = v0 ? ex2f(fmaf(x0, c, nmc)) : 0.f;
-            const float p1 = v1 ? ex2f(fmaf(x1, c, nmc)) : 0.f;
-            ls += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const int u = (cc >> 3) + qd;
-            st_shared_v4(p_row + ((u ^ rx) << 4), pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-          }
-        }
-      }
-      return ls;
-    };
-    auto rescale_o = [&](float f) {
-      for (int cc = 0; cc < p.dpad; cc += 16) {
-        uint32_t r[16];
-        tmem_ld16_nowait(o_tmem + lane_off + cc, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-        tmem_st16(o_tmem + lane_off + cc, r);
-      }
-      tmem_wait_st();
-    };
-    // every P V issued so far has retired: O may be read / rescaled (tile j-1 was the last one handed to the MMA warp)
-    auto wait_o_quiescent = [&](int j) {
-      if (j > 0) { mbar_wait(p_free((j - 1) & 1), ((j - 1) >> 1) & 1); tc_fence_after(); }
-    };
-
-    for (int j = 0; j < T; ++j) {
-      const int n_valid = min(A2_BKV, p.M - j * A2_BKV);
-      const int bsel = j & 1;
-      const uint32_t s_tmem = tmem_base + (uint32_t)bsel * 64u;
-      const uint32_t pbuf = p_smem + (uint32_t)bsel * AT_CHUNK;
-      const bool spec = j > 0 && n_valid == A2_BKV;
-      mbar_wait(s_full(bsel), (j >> 1) & 1);
-      tc_fence_after();
-      if (!spec) {
-        const float m_new = fmaxf(m_used, tile_max(s_tmem, n_valid));
-        const bool need = (m_new - m_used) * c > 8.f;
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
-          wait_o_quiescent(j);
-          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
-          rescale_o(f);
-          l_run *= f;
-        }
-        if (need) m_used = m_new;
-      }
-      mbar_wait(p_free(bsel), ((j >> 1) & 1) ^ 1);     // P V of tile j-2 retired: this P buffer is ours again
-      float mx = -INFINITY;
-      float l_tile = tile_exp(s_tmem, pbuf, n_valid, m_used, mx);
-      if (spec) {
-        const float m_new = fmaxf(m_used, mx);
-        const bool need = (m_new - m_used) * c > 8.f;
-        if (__any_sync(0xffffffffu, need)) {           // rare: this tile raised the max by more than 2^8 -> redo it
-          wait_o_quiescent(j);
-          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
-          rescale_o(f);
-          l_run *= f;
-          if (need) m_used = m_new;
-          l_tile = tile_exp(s_tmem, pbuf, n_valid, m_used, mx);
-        }
-      }
-      l_run += l_tile;
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(bsel));
-    }
-    mbar_wait(o_done, 0);
-    tc_fence_after();
-    const int q = q0 + row;
-    const float inv = 1.f / l_run;
-    const int C = p.H * p.d;
-    bf16* orow = p.o + ((long)b * p.N + q) * C + h * p.d;
-    for (int cc = 0; cc < p.dpad; cc += 16) {
-      uint32_t r[16];
-      tmem_ld16_nowait(o_tmem + lane_off + cc, r);
-      tmem_wait_ld();
-      if (q < p.N) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (cc + 8 * hh < p.d) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r[8 * hh + 0]) * inv, __uint_as_float(r[8 * hh + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(r[8 * hh + 2]) * inv, __uint_as_float(r[8 * hh + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(r[8 * hh + 4]) * inv, __uint_as_float(r[8 * hh + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(r[8 * hh + 6]) * inv, __uint_as_float(r[8 * hh + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + cc + 8 * hh) = o;
-          }
-        }
-      }
-    }
-    if (q < p.N && p.lse) p.lse[((long)b * p.H + h) * p.N + q] = m_used * p.scale + logf(l_run);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
-  }
-}
-
 // head-sliced view of a [B, len, >= H*d] bf16 tensor with row stride ld elements (ld = H*d when dense; 3*H*d for
 // the q/k/v thirds of a packed projection output): dims (d, H, len, B)
 static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int len, int B, long ld, int rows = 128) {
@@ -669,46 +387,18 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.o = (bf16*)o; p.lse = lse;
   p.wait_hint = tc_wait_hint_ns();
   CUtensorMap tq, tk, tv;
-  // SIDLSG_ATTN_FWD_V2=1 selects the 64-key double-buffered kernel.  Measured on B200 (B8 N4096 d40): 0.632 ms vs
-  // 0.558 ms for the 128-key kernel - the softmax loop is bound by its own MUFU / TMEM-read / issue work, not by waiting
-  // for the tensor pipe, so halving the tile only doubles the per-tile barrier cost.  Kept as a tested A/B variant.
-  static int fwd_gen = -1;
-  if (fwd_gen < 0) { const char* e = getenv("SIDLSG_ATTN_FWD_V2"); fwd_gen = (e && e[0] == '1') ? 2 : 1; }
-  if (fwd_gen == 2 && p.dpad <= 128) {
-    if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk, A2_BKV) ||
-        !make_head_map(&tv, v, d, H, M, B, ldv, A2_BKV))
-      return SIDLSG_ERR_CUDA;
-    // ring depth: as many 64-key K/V stages as fit beside Q and the two P buffers (2 CTAs/SM when the total <= 113 KB)
-    p.kv_stages = p.dchunks == 1 ? 4 : 3;
-    const int smem2 = p.dchunks * AT_CHUNK + 2 * p.kv_stages * p.dchunks * A2_KVCHUNK + 2 * AT_CHUNK + 256;
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      attr2 = true;
-    }
-    dim3 grid2((N + AT_BQ - 1) / AT_BQ, H, B);
-    attn_fwd2_kernel<0><<<grid2, AT_THREADS, smem2, st>>>(tq, tk, tv, p);
-    return check_launch("attention_fwd");
-  }
   if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
       !make_head_map(&tv, v, d, H, M, B, ldv))
     return SIDLSG_ERR_CUDA;
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
   if (!g_attn_attr_done) {
-    cudaFuncSetAttribute(attn_fwd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_attr_done = true;
   }
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
-  if (tc_elect_enabled()) {
-    if (p.dpad <= 128) attn_fwd_kernel<256, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-    else attn_fwd_kernel<512, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  } else {
-    if (p.dpad <= 128) attn_fwd_kernel<256, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-    else attn_fwd_kernel<512, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  }
+  if (p.dpad <= 128) attn_fwd_kernel<256><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   return check_launch("attention_fwd");
 }
 
@@ -743,7 +433,6 @@ struct AttnBwdParams {
   long lddk, lddv;       // row strides (elements) of dk / dv
 };
 
-template <bool ELECT>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -798,7 +487,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       mbar_expect_tx(kv_full, 2 * tile_bytes);
       for (int c = 0; c < p.dchunks; ++c) {
         tma_load_4d(&tmK, kv_full, k_smem + c * AT_CHUNK, c * 64, h, kv0, b);
@@ -816,7 +505,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       const int dsteps = p.dpad >> 4;
       const uint32_t idesc_s = make_idesc(128, 0, 0);
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
@@ -1158,13 +847,11 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256 +
                    (p.stage_alias ? 0 : ((d + 31) / 32) * AT_CHUNK);
   if (!g_attn_bwd_attr_done) {
-    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_bwd_attr_done = true;
   }
   dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
-  if (tc_elect_enabled()) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
-  else attn_bwd_kernel<false><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;
   // dq (bf16) = dq_acc (fp32)

@@ -127,7 +127,7 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   return t;
 }
 
-template <bool BM2, bool ELECT>
+template <bool BM2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -176,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
@@ -242,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (role_leader<ELECT>(lane)) {
+    if (role_leader()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -601,11 +601,6 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
 static int g_tc_state = -1;   // -1 unknown, 0 off, 1 on
 static int g_num_sms = 148;
 int tc_num_sms() { return g_num_sms; }
-bool tc_elect_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SIDLSG_ELECT"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
 unsigned tc_wait_hint_ns() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SIDLSG_WAIT_HINT_NS"); v = e ? atoi(e) : 100; if (v < 0) v = 0; }
@@ -621,10 +616,8 @@ bool tc_enabled() {
               cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10 && get_encode() != nullptr;
     if (ok) {
       g_num_sms = prop.multiProcessorCount;
-      ok = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+      ok = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     }
     cudaGetLastError();
     g_tc_state = ok ? 1 : 0;
@@ -810,13 +803,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
   plan_stages(p);
-  if (tc_elect_enabled()) {
-    if (p.bm2) gemm_tc_kernel<true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
-    else gemm_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
-  } else {
-    if (p.bm2) gemm_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
-    else gemm_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
-  }
+  if (p.bm2) gemm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
+  else gemm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc");
 }
 

@@ -97,13 +97,9 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\nselp.u32 %0, 1, 0, e;\n}" : "=r"(pred));
   return pred != 0;
 }
-// role leader of a single-thread role (TMA producer, MMA issuer): ELECT = the elect.sync form (opt-in until validated on
-// a GPU: SIDLSG_ELECT=1), otherwise lane 0
-template <bool ELECT>
-__device__ __forceinline__ bool role_leader(int lane) {
-  if constexpr (ELECT) return elect_one();
-  else return lane == 0;
-}
+// role leader of a single-thread role (TMA producer, MMA issuer).  Validated on B200 in round 2
+// (profiles/r02_ubench_mma_issue_b200.txt: 81-171 cycles per MMA against a flat 184 for the `lane == 0` form, which is gone).
+__device__ __forceinline__ bool role_leader() { return elect_one(); }
 
 // named barrier among `n` threads (ids 1.. ; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -205,7 +201,5 @@ bool tc_enabled();
 int tc_num_sms();
 // SIDLSG_WAIT_HINT_NS (default 100; 0 = plain polling): suspend-time hint of the mbarrier waits of the TMA / MMA helper warps
 unsigned tc_wait_hint_ns();
-// SIDLSG_ELECT=1: kernels instantiated with elect.sync role leaders (see elect_one)
-bool tc_elect_enabled();
 
 }  // namespace sidlsg

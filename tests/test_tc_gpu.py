@@ -269,31 +269,6 @@ def test_tma_store_switch_matches():
     assert outs[0] == outs[1], outs
 
 
-def test_attention_fwd_v2_switch():
-    """the 64-key double-buffered forward (SIDLSG_ATTN_FWD_V2=1) agrees with the default kernel."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import torch, sys; sys.path.insert(0, %r)\n"
-        "from sid_lsg_b200 import ops\n"
-        "g = torch.Generator().manual_seed(0)\n"
-        "q = torch.randn(2, 1024, 320, generator=g).cuda().bfloat16()\n"
-        "k = torch.randn(2, 333, 320, generator=g).cuda().bfloat16()\n"
-        "v = torch.randn(2, 333, 320, generator=g).cuda().bfloat16()\n"
-        "o = ops.attention(q, k, v, 8)\n"
-        "torch.cuda.synchronize(); print(float(o.float().double().sum()), float(o.float().abs().double().sum()))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for flag in ("0", "1"):
-        env = dict(os.environ, SIDLSG_ATTN_FWD_V2=flag)
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append([float(x) for x in r.stdout.strip().splitlines()[-1].split()])
-    assert abs(outs[0][1] - outs[1][1]) <= 2e-3 * abs(outs[0][1]), outs
-    assert abs(outs[0][0] - outs[1][0]) <= 2e-3 * abs(outs[0][1]), outs
-
-
 def test_bm2_tiles_match():
     """256-row tiles (two A tiles per B tile, SIDLSG_BM2=2 forces them) == 128-row tiles, bit for bit: the reduction
     order of every output element is the same, only the tile shape differs."""
@@ -334,49 +309,3 @@ def test_bm2_tiles_match():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1], outs
-
-
-@pytest.mark.skipif(__import__("os").environ.get("SIDLSG_TEST_ELECT") != "1",
-                    reason="opt-in: elect.sync role leaders (SIDLSG_ELECT=1) have not been validated on hardware yet")
-def test_elect_role_leaders_match():
-    """kernels instantiated with elect.sync role leaders == the lane-0 instantiations, bit for bit (same instructions
-    issued by the same single thread; only the code generated around them differs)."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import torch, sys, math; sys.path.insert(0, %r)\n"
-        "from sid_lsg_b200 import ops\n"
-        "g = torch.Generator().manual_seed(0)\n"
-        "def P(t, cl=False):\n"
-        "    t = t.cuda()\n"
-        "    if cl: t = t.contiguous(memory_format=torch.channels_last)\n"
-        "    p = torch.nn.Parameter(t); p._shadow = p.detach().bfloat16(); p.grad = torch.zeros_like(p); return p\n"
-        "out = []\n"
-        "x = torch.randn(4096, 1280, generator=g).cuda().bfloat16().requires_grad_(True)\n"
-        "w = P(torch.randn(640, 1280, generator=g) / 36)\n"
-        "y = ops.linear(x, w, torch.randn(640, generator=g).cuda(), None)\n"
-        "y.backward(torch.randn(4096, 640, generator=g).cuda().bfloat16())\n"
-        "out += [y.float().abs().double().sum().item(), x.grad.float().abs().double().sum().item(), w.grad.abs().double().sum().item()]\n"
-        "xc = torch.randn(4, 16, 16, 128, generator=g).cuda().bfloat16().requires_grad_(True)\n"
-        "wc = P(torch.randn(320, 128, 3, 3, generator=g) / 34, True)\n"
-        "yc = ops.conv3x3(xc, wc, torch.randn(320, generator=g).cuda())\n"
-        "yc.backward(torch.randn(yc.shape, generator=g).cuda().bfloat16())\n"
-        "out += [yc.float().abs().double().sum().item(), xc.grad.float().abs().double().sum().item(), wc.grad.abs().double().sum().item()]\n"
-        "q = torch.randn(2, 1024, 320, generator=g).cuda().bfloat16().requires_grad_(True)\n"
-        "k = torch.randn(2, 333, 320, generator=g).cuda().bfloat16().requires_grad_(True)\n"
-        "v = torch.randn(2, 333, 320, generator=g).cuda().bfloat16().requires_grad_(True)\n"
-        "o = ops.attention(q, k, v, 8)\n"
-        "o.backward(torch.randn(o.shape, generator=g).cuda().bfloat16())\n"
-        "out += [o.float().abs().double().sum().item(), q.grad.float().abs().double().sum().item(), k.grad.float().abs().double().sum().item(), v.grad.float().abs().double().sum().item()]\n"
-        "torch.cuda.synchronize(); print(' '.join(repr(t) for t in out))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for flag in ("0", "1"):
-        env = dict(os.environ, SIDLSG_ELECT=flag)
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append([float(t) for t in r.stdout.strip().splitlines()[-1].split()])
-    # GEMM / conv / attention forward are bit-identical; the split-K and dQ reductions use fp32 atomics (order-dependent)
-    for a, b in zip(outs[0], outs[1]):
-        assert abs(a - b) <= 1e-4 * abs(a), outs
