@@ -50,6 +50,17 @@ def parse():
     return ap.parse_args()
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -99,9 +110,11 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_oracle_iteration_time(args, budget_s, steps, warmup):
+def cpu_oracle_iteration_time(args, budget_s, steps, warmup, parity=None):
     """The reference's algorithm (oracle restatement: pure torch.nn fp32, TF32 off, per-sample x0 loop, torch Adam)
-    on this host's cores: one SiD-LSG iteration at batch 1 per step.  Returns (images/s, ms/step, steps run, cores)."""
+    on this host's cores: one SiD-LSG iteration at batch 1 per step.  Returns (images/s, ms/step, steps run, cores).
+    `parity` (dict, optional) receives the first (warm-up) iteration's inputs, initial weights and results, which the
+    caller replays on the GPU path to MEASURE the benchmarked mode's deviation from the fp32 reference arithmetic."""
     import oracle
     from oracle import step as ostep
     cores = os.cpu_count() or 1
@@ -124,10 +137,18 @@ def cpu_oracle_iteration_time(args, budget_s, steps, warmup):
     while True:
         mb_f = [ostep.synth_microbatch(1, cfg, 1000 + i, dropout=True, num_steps=args.num_steps)]
         mb_g = [ostep.synth_microbatch(1, cfg, 2000 + i, num_steps=args.num_steps)]
+        if parity is not None and i == 0:
+            parity["init"] = {k: v.clone() for k, v in true_score.state_dict().items()}
+            parity["mb_f"], parity["mb_g"] = mb_f, mb_g
+            with torch.no_grad():
+                parity["latents"] = ostep.sampler(true_score, sched, mb_g[0]["z"], mb_g[0]["cond"], torch.full((1,), 625),
+                                                  num_steps=args.num_steps, sub_noise=mb_g[0].get("sub_noise"))
         t0 = time.perf_counter()
-        ostep.iteration(G, None, fake, true_score, sched, opt_f, opt_g, mb_f, mb_g, kappa=args.kappa, batch_size=1,
-                        num_steps=args.num_steps)
+        lf, lg = ostep.iteration(G, None, fake, true_score, sched, opt_f, opt_g, mb_f, mb_g, kappa=args.kappa,
+                                 batch_size=1, num_steps=args.num_steps)
         dt = time.perf_counter() - t0
+        if parity is not None and i == 0:
+            parity["loss_fake"], parity["loss_G"] = float(lf), float(lg)
         i += 1
         if done_warm < min(warmup, 1):
             done_warm += 1
@@ -144,12 +165,13 @@ def run_reference(args, rank):
     if rank != 0:
         return
     v, ms, n, cores = cpu_oracle_iteration_time(args, args.cpu_budget_s, args.steps, args.warmup)
-    sample = ("1 full SiD-LSG iteration (f_psi + G_theta updates, Adam) at batch 1, %s fp32, 64x64x4 latents, per step; "
-              "%d of the requested %d steps fit the %.0f s CPU budget" % (args.model, n, args.steps, args.cpu_budget_s))
+    sample = ("each step = 1 full SiD-LSG iteration (f_psi + G_theta updates, Adam) at BATCH 1 (not the workload's batch "
+              "%d: a bounded sample, images/s = 1 / step time), %s fp32, 64x64x4 latents; %d of the requested %d steps fit "
+              "the %.0f s CPU budget" % (args.batch, args.model, n, args.steps, args.cpu_budget_s))
     line = {"impl": "reference", "metric": "SiD-LSG train images/sec", "value": v, "unit": "images/s",
             "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": dict(workload_config(args, 1), sample_batch=1),
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -322,7 +344,7 @@ def main():
         ach = work / (ms / 1e3) / 1e12 if ms > 0 else 0.0
         line["roofline"] = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv3x3: linear+conv fwd, dgrad, wgrad)",
                             "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops_sustained"],
-                            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": None,
+                            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": load_traffic(),
                             "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                             "launches": n, "avg_launch_ms": round(ms / max(n, 1), 4),
                             "algorithmic_flop_per_launch": work / max(n, 1), "share_of_step": round(ms / ms_step, 4),
@@ -341,14 +363,47 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del resident
         torch.cuda.empty_cache()
+        del st, true_score, fake, G, G_ema, base
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        parity = {}
         try:
-            v, ms, n, cores = cpu_oracle_iteration_time(args, min(args.cpu_budget_s, 150.0), 2, 1)
+            v, ms, n, cores = cpu_oracle_iteration_time(args, min(args.cpu_budget_s, 150.0), 2, 1, parity=parity)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "%d timed SiD-LSG iteration(s) at batch 1 (%s fp32 oracle, 64x64x4 latents) after 1 warm-up; %.1f s per iteration"
                                               % (n, args.model, ms / 1e3)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (e,)}
+        # ---- measured deviation of the benchmarked arithmetic from the fp32 reference arithmetic --------------------
+        # the oracle's warm-up iteration (weights, inputs, losses, generated latents) replayed through the CUDA path in
+        # the benchmarked dtype: relative errors, printed rather than assumed
+        if "loss_G" in parity:
+            try:
+                nets = []
+                for _ in range(3):
+                    m = S.UNet2DConditionModel(cfg, compute_dtype=cd)
+                    m.load_state_dict(parity["init"])
+                    nets.append(m.to(dev).flatten_())
+                pst = S.SiDLSGStep(nets[0], nets[1], nets[2], None, S.DDPMScheduler(device=dev), cfg_train_fake=args.kappa,
+                                   cfg_eval_fake=args.kappa, cfg_eval_real=args.kappa, num_steps=args.num_steps,
+                                   ema_halflife_kimg=0)
+                mg = to_device(parity["mb_g"][0], dev)
+                with torch.no_grad():
+                    img = S.sid_sd_sampler(pst.true_score, mg["z"], S.PromptBatch(mg["cond"], mg["uncond"]),
+                                           torch.full((1,), 625, device=dev), pst.sched, num_steps=args.num_steps,
+                                           sub_noise=mg.get("sub_noise"))
+                lf, lg = pst.iteration([to_device(m, dev) for m in parity["mb_f"]],
+                                       [to_device(m, dev) for m in parity["mb_g"]], batch_size=1)
+                ref = parity["latents"]
+                line["parity_rel_err"] = {
+                    "mode": args.dtype, "against": "oracle fp32 iteration at batch 1, same weights and inputs",
+                    "latents": float((img.cpu() - ref).norm() / ref.norm()),
+                    "loss_fake": abs(float(lf[0].item()) - parity["loss_fake"]) / abs(parity["loss_fake"]),
+                    "loss_G": abs(float(lg[0].item()) - parity["loss_G"]) / max(abs(parity["loss_G"]), 1e-30)}
+            except Exception as e:  # noqa: BLE001
+                line["parity_rel_err"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

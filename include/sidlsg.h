@@ -171,12 +171,35 @@ int sidlsg_lsg_loss(const float* xg, const float* yreal, const float* yfake, flo
 /* ---- fused optimiser pass over a flat fp32 bucket (n % 4 == 0) ------------------------------------------------
  * g <- nan_to_num(g * grad_scale, 0, 1e5, -1e5) [clip to +-clip if clip > 0]; Adam(beta1, beta2, eps) with
  * torch.optim.Adam bias correction at `step`; optional decoupled weight decay; optional EMA
- * ema <- p + ema_beta (ema - p) after the step; optional bf16 shadow of p. m may be null when beta1 == 0.
+ * ema <- p + ema_beta (ema - p) after the step; optional bf16 shadows of p and of ema (the copies the tensor-core
+ * GEMMs of G and G_ema read). m may be null when beta1 == 0.
  * ref: training/sid_training_loop.py:458-462, 541-549, 553-565; sid_train.py:219-226. */
-int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16, long n,
+int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
+                     void* ema_shadow_bf16, long n,
                      float lr, float beta1, float beta2, float eps, int step, float grad_scale, float clip,
                      float ema_beta, float weight_decay, void* stream);
 int sidlsg_ema_update(const float* p, float* ema, long n, float beta, void* stream);
+
+/* ---- fp32-accurate tensor-core mode (csrc/split3.cu) --------------------------------------------------------
+ * The same contractions for fp32 operands and fp32 outputs, computed on tcgen05 as three bf16 passes
+ * (A_hi B_hi + A_hi B_lo + A_lo B_hi, fp32 accumulation): the parity instrument for the reference's fp32 / TF32-off
+ * path (ref: training/sid_training_loop.py:241-243) that exercises the benchmarked kernel.  `ws` is caller-provided
+ * scratch of sidlsg_split3_ws_bytes(a_elems, b_elems) bytes (elements of the two operands; GEMM: nb1*nb2*rows*ceil8(K)).
+ * SIDLSG_ERR_UNSUPPORTED = shape not eligible for the tensor-core kernel: use the plain entry point. */
+long sidlsg_split3_ws_bytes(long a_elems, long b_elems);
+int sidlsg_gemm_split3(const float* a, long a_sm, long a_sk, long a_sb1, long a_sb2,
+                       const float* b, long b_sn, long b_sk, long b_sb1, long b_sb2,
+                       float* c, long ldc, long c_sb1, long c_sb2,
+                       const float* bias, const float* res, long ldr, long r_sb1, long r_sb2,
+                       const float* rowvec, int rows_per_vec, float alpha, int accumulate,
+                       int M, int N, int K, int nb1, int nb2, void* ws, long ws_bytes, void* stream);
+int sidlsg_conv3x3_split3(const float* x, const float* w, long w_elems, float* y, const float* bias,
+                          const float* res, const float* rowvec, int B, int Hi, int Wi, int Kc, int Ho,
+                          int Wo, int N, long w_sn, long w_stap, long w_sk, int stride, int flip,
+                          void* ws, long ws_bytes, void* stream);
+int sidlsg_conv3x3_wgrad_split3(const float* x, const float* dy, float* dw, int B, int Hi, int Wi, int Cin,
+                                int Ho, int Wo, int Cout, long dw_sco, long dw_stap, long dw_sci, int stride,
+                                void* ws, long ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

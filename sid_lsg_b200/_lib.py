@@ -73,6 +73,18 @@ class _Lib:
         self.load()
         return self._fns["sidlsg_last_error"]().decode()
 
+    def try_call(self, name, *args):
+        """like call(), but returns False instead of raising when the entry point reports SIDLSG_ERR_UNSUPPORTED
+        (shape not eligible for that kernel: the caller then uses the general entry point)."""
+        self.load()
+        st = self._fns["sidlsg_" + name](*args)
+        if st == -3:
+            return False
+        if st != 0:
+            raise RuntimeError("sidlsg_%s failed (%d): %s" % (name, st, self.last_error()))
+        self.launches += 1
+        return True
+
     def call(self, name, *args):
         self.load()
         timer = self.timer
@@ -117,9 +129,10 @@ class KernelTimer:
         def gn_bwd(a):    # B, HW, C at 13..15; read dy,x twice, write dx
             return ("byte", 5.0 * a[13] * a[14] * a[15] * (4 if a[19] == 0 else 2))
 
-        def adam(a):      # p,g,m,v,ema,shadow,n: read p,g,v(,ema) write p,v(,ema,shadow)
-            n = a[6]
-            return ("byte", n * (20.0 + (8 if a[4] else 0) + (2 if a[5] else 0) + (8 if a[2] else 0)))
+        def adam(a):      # p,g,m,v,ema,shadow,ema_shadow,n: read p,g,v(,ema) write p,v(,ema,shadows)
+            n = a[7]
+            return ("byte", n * (20.0 + (8 if a[4] else 0) + (2 if a[5] else 0) + (2 if (a[4] and a[6]) else 0) +
+                                 (8 if a[2] else 0)))
 
         def lsg(a):       # B, CHW at 7,8: 3 reads + 3 writes fp32
             return ("byte", 24.0 * a[7] * a[8])

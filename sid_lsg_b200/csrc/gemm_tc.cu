@@ -900,13 +900,13 @@ int tc_gemm_try(const void* a, long a_sm, long a_sk, long a_sb1, long a_sb2, con
 }
 
 // tile shape of the implicit-GEMM convolution (forward / data gradient)
-static void plan_conv(TcParams& p, long M, int N, int Kc, bool dgrad) {
+static void plan_conv(TcParams& p, long M, int N, int Kc, bool dgrad, bool allow_bm2 = true) {
   p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   const int kbt = 9 * (Kc / 64);
   const GridTiling t1 = pick_block_n_grid(N, dgrad, p.m_tiles, kbt);
   p.block_n = t1.bn;
   const int mode = bm2_mode();
-  if (mode && M >= 256 && (M % (2 * TC_BM)) == 0) {
+  if (mode && allow_bm2 && M >= 256 && (M % (2 * TC_BM)) == 0) {
     const long mt2 = M / (2 * TC_BM);
     const GridTiling t2 = pick_block_n_grid(N, dgrad, mt2, kbt, true);
     if (mode == 2 || (M >= 512 && t2.cost < t1.cost * 0.95)) { p.bm2 = 1; p.block_n = t2.bn; p.m_tiles = (int)mt2; }
@@ -931,8 +931,11 @@ static bool conv_box(int H, int W, int pixels, uint32_t* wt, uint32_t* ht, uint3
 int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec,
                    int B, int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride,
                    int up, int transposed, int flip, int accumulate, int in_dtype, int out_dtype, cudaStream_t st) {
-  if (!tc_enabled() || in_dtype != SIDLSG_BF16 || out_dtype != SIDLSG_BF16) return 0;
-  if ((stride != 1 && stride != 2) || up != 1 || transposed || accumulate) return 0;
+  if (!tc_enabled() || in_dtype != SIDLSG_BF16) return 0;
+  // fp32 output (plain or atomic-add) serves the fp32-accurate 3 x bf16 mode (split3.cu); the bf16 path never accumulates
+  if (out_dtype != SIDLSG_BF16 && out_dtype != SIDLSG_F32) return 0;
+  if (accumulate == 1 || (accumulate == 2 && out_dtype != SIDLSG_F32)) return 0;
+  if ((stride != 1 && stride != 2) || up != 1 || transposed) return 0;
   if ((Kc % 64) || (N % 8) || !aligned16(x) || !aligned16(w)) return 0;
   const bool fwd = !flip && w_sk == 1 && w_stap == Kc && w_sn == 9L * Kc;
   const bool dgrad = flip && w_sn == 1 && w_stap == N && w_sk == 9L * N;
@@ -948,7 +951,7 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = N;
-  plan_conv(p, M, N, Kc, dgrad);
+  plan_conv(p, M, N, Kc, dgrad, out_dtype == SIDLSG_BF16);   // 256-row tiles: bf16 outputs only (as plan_dense)
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.splits = 1;
   p.cchunks = Kc / 64;
@@ -956,7 +959,7 @@ int tc_conv3x3_try(const void* x, const void* w, void* y, const float* bias, con
   p.a_mode = A_CONV;
   p.b_mode = fwd ? B_K2D : B_W3D;
   p.H = Ho; p.W = Wo; p.flip = flip; p.cstride = stride;
-  p.c = y; p.ldc = N; p.out_f32 = 0;
+  p.c = y; p.ldc = N; p.out_f32 = out_dtype == SIDLSG_F32; p.atomic = accumulate == 2;
   p.bias = bias; p.res = res; p.ldr = N; p.rowvec = rowvec; p.rows_per_vec = Ho * Wo; p.alpha = 1.f;
 
   CUtensorMap ta, tb;

@@ -5,7 +5,7 @@
 //   clip (fp16) /root/reference/training/sid_training_loop.py:546-547
 //   Adam        /root/reference/sid_train.py:219-226 (betas (0, 0.999), eps 1e-8) = torch.optim.Adam semantics
 //   EMA         /root/reference/training/sid_training_loop.py:553-565  (p_ema <- p + beta (p_ema - p), after the step)
-// HBM-bound: reads p, g, v (+m, +ema), writes p, v (+m, +ema, +bf16 shadow): 24-34 B per parameter.
+// HBM-bound: reads p, g, v (+m, +ema), writes p, v (+m, +ema, +bf16 shadows of p and ema): 24-36 B per parameter.
 #include "common.cuh"
 
 namespace sidlsg {
@@ -17,6 +17,7 @@ struct AdamArgs {
   float* v;
   float* ema;     // null: no EMA
   bf16* shadow;   // null: no bf16 shadow
+  bf16* ema_shadow;  // null: the EMA network keeps no bf16 shadow
   long n;
   float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, clip, ema_beta, weight_decay;
 };
@@ -61,6 +62,13 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
       pk.y = *reinterpret_cast<unsigned*>(&hi);
       reinterpret_cast<uint2*>(a.shadow)[i] = pk;
     }
+    if (a.ema && a.ema_shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(e.x, e.y), hi = __floats2bfloat162_rn(e.z, e.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&lo);
+      pk.y = *reinterpret_cast<unsigned*>(&hi);
+      reinterpret_cast<uint2*>(a.ema_shadow)[i] = pk;
+    }
   }
 }
 
@@ -84,7 +92,8 @@ __global__ void __launch_bounds__(256) ema_kernel(const float* __restrict__ p, f
 using namespace sidlsg;
 
 // n must be a multiple of 4 (the flat bucket is padded).  step >= 1 is the Adam step count AFTER this update.
-extern "C" int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16, long n,
+extern "C" int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
+                                void* ema_shadow_bf16, long n,
                                 float lr, float beta1, float beta2, float eps, int step, float grad_scale, float clip,
                                 float ema_beta, float weight_decay, void* stream) {
   if (n % 4) { set_error("adam_step: n=%ld not a multiple of 4", n); return SIDLSG_ERR_ARG; }
@@ -92,7 +101,8 @@ extern "C" int sidlsg_adam_step(float* p, const float* g, float* m, float* v, fl
   if (beta1 != 0.f && !m) { set_error("adam_step: beta1 != 0 needs the m buffer"); return SIDLSG_ERR_ARG; }
   if (n == 0) return SIDLSG_OK;
   AdamArgs a;
-  a.p = p; a.g = g; a.m = (beta1 != 0.f) ? m : nullptr; a.v = v; a.ema = ema; a.shadow = (bf16*)shadow_bf16; a.n = n;
+  a.p = p; a.g = g; a.m = (beta1 != 0.f) ? m : nullptr; a.v = v; a.ema = ema; a.shadow = (bf16*)shadow_bf16;
+  a.ema_shadow = (bf16*)ema_shadow_bf16; a.n = n;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));

@@ -7,6 +7,8 @@ Weight gradients are accumulated by the wgrad kernels straight into `param.grad`
 gradient bucket, see params.FlatParams) and the Functions return None for them: no temporary, no extra pass,
 and the bucket is what the data-parallel allreduce and the fused optimiser consume.
 """
+import contextlib
+
 import torch
 from torch.autograd import Function
 
@@ -17,10 +19,38 @@ FLASH_ATTENTION = True         # bf16 mode: tcgen05 flash attention forward (att
 FLASH_ATTENTION_BWD = True     # ... and backward (d <= 80; d = 160 layers use the recompute path)
 
 
+# ---- fp32-accurate tensor-core mode (csrc/split3.cu) ---------------------------------------------------------
+_SPLIT = [False]
+
+
+@contextlib.contextmanager
+def tc_split(on=True):
+    """While active, fp32 Linear / conv3x3 / attention contractions run on tcgen05 as three bf16 passes (x = hi + lo)
+    instead of the CUDA-core kernels; each autograd Function remembers the setting of its forward for its backward."""
+    prev, _SPLIT[0] = _SPLIT[0], bool(on)
+    try:
+        yield
+    finally:
+        _SPLIT[0] = prev
+
+
+def split_active():
+    return _SPLIT[0]
+
+
+def _split_ws(a_elems, b_elems, device):
+    n = lib.query("split3_ws_bytes", a_elems, b_elems)
+    return torch.empty((n,), dtype=torch.uint8, device=device), n
+
+
 def _grad_of(p):
     """fp32 gradient buffer of a Parameter, laid out exactly like the parameter."""
     if p.grad is None:
-        p.grad = torch.zeros_like(p, dtype=torch.float32)  # preserve_format keeps the physical layout
+        flat = getattr(p, "_flat", None)
+        if flat is not None:
+            flat.ensure_grad()             # points every parameter's .grad at its slice of the flat bucket
+        else:
+            p.grad = torch.zeros_like(p, dtype=torch.float32)  # preserve_format keeps the physical layout
     return p.grad
 
 
@@ -30,7 +60,15 @@ def _c(t):
 
 def gemm(a, a_sm, a_sk, b, b_sn, b_sk, c, ldc, M, N, K, *, a_sb=(0, 0), b_sb=(0, 0), c_sb=(0, 0), nb=(1, 1),
          bias=None, res=None, ldr=0, r_sb=(0, 0), rowvec=None, rows_per_vec=1, alpha=1.0, accumulate=0,
-         in_dtype=None, out_dtype=None):
+         in_dtype=None, out_dtype=None, split=False):
+    if split and a.dtype == torch.float32 and b.dtype == torch.float32 and c.dtype == torch.float32 and accumulate != 1:
+        Kp = (K + 7) // 8 * 8
+        nbz = nb[0] * nb[1]
+        ws, n = _split_ws(nbz * M * Kp, nbz * N * Kp, a.device)
+        if lib.try_call("gemm_split3", ptr(a), a_sm, a_sk, a_sb[0], a_sb[1], ptr(b), b_sn, b_sk, b_sb[0], b_sb[1],
+                        ptr(c), ldc, c_sb[0], c_sb[1], ptr(bias), ptr(res), ldr, r_sb[0], r_sb[1], ptr(rowvec),
+                        rows_per_vec, alpha, accumulate, M, N, K, nb[0], nb[1], ptr(ws), n, stream()):
+            return
     lib.call("gemm", ptr(a), a_sm, a_sk, a_sb[0], a_sb[1], ptr(b), b_sn, b_sk, b_sb[0], b_sb[1],
              ptr(c), ldc, c_sb[0], c_sb[1], ptr(bias), ptr(res), ldr, r_sb[0], r_sb[1], ptr(rowvec), rows_per_vec,
              alpha, accumulate, M, N, K, nb[0], nb[1], dt(a) if in_dtype is None else in_dtype,
@@ -52,7 +90,8 @@ class LinearFn(Function):
         y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
         if res is not None:
             res = _c(res)
-        gemm(x, K, 1, wc, K, 1, y, N, M, N, K, bias=bias, res=res, ldr=N)
+        ctx.split = _SPLIT[0]
+        gemm(x, K, 1, wc, K, 1, y, N, M, N, K, bias=bias, res=res, ldr=N, split=ctx.split)
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, wc)
         ctx.weight, ctx.bias = owner  # the Parameter objects themselves (their .grad is the flat-bucket view)
         ctx.dims = (M, N, K)
@@ -66,9 +105,9 @@ class LinearFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(dy.shape[:-1] + (K,), dtype=dy.dtype, device=dy.device)
-            gemm(dy, N, 1, wc, 1, K, dx, K, M, K, N)
+            gemm(dy, N, 1, wc, 1, K, dx, K, M, K, N, split=ctx.split)
         if ctx.needs_input_grad[1]:
-            gemm(dy, 1, N, x, 1, K, _grad_of(ctx.weight), K, N, K, M, accumulate=2, out_dtype=F32)
+            gemm(dy, 1, N, x, 1, K, _grad_of(ctx.weight), K, N, K, M, accumulate=2, out_dtype=F32, split=ctx.split)
         if ctx.bias is not None and ctx.needs_input_grad[3]:
             lib.call("colsum", ptr(dy), ptr(_grad_of(ctx.bias)), 1, M, N, 1, dt(dy), stream())
         return dx, None, None, None, (dy if ctx.needs_input_grad[4] else None), None
@@ -98,8 +137,13 @@ class FusedWeight:
         self.flat = flat
         self.shape = (n, K)
         self.master = flat.master[off:off + n * K].view(n, K)
-        self.grad = flat.grad[off:off + n * K].view(n, K)
+        self._span = (off, n * K)
         self._shadow = flat.shadow[off:off + n * K].view(n, K) if flat.shadow is not None else None
+
+    @property
+    def grad(self):
+        off, n = self._span
+        return self.flat.ensure_grad()[off:off + n].view(self.shape)
 
     def compute(self, dtype):
         return self.master if dtype == torch.float32 else self._shadow
@@ -141,8 +185,15 @@ class Conv3x3Fn(Function):
         if rowvec is not None:
             rowvec = _c(rowvec)
             assert rowvec.dtype == torch.float32 and rowvec.shape == (B, N)
-        lib.call("conv3x3", ptr(x), ptr(wc), ptr(y), ptr(bias), ptr(res), ptr(rowvec), B, H, W, C, Ho, Wo, N,
-                 9 * C, C, 1, stride, up, 0, 0, 0, dt(x), dt(y), stream())
+        ctx.split = _SPLIT[0] and x.dtype == torch.float32
+        done = False
+        if ctx.split and up == 1:
+            ws, n = _split_ws(x.numel(), wc.numel(), x.device)
+            done = lib.try_call("conv3x3_split3", ptr(x), ptr(wc), wc.numel(), ptr(y), ptr(bias), ptr(res), ptr(rowvec),
+                                B, H, W, C, Ho, Wo, N, 9 * C, C, 1, stride, 0, ptr(ws), n, stream())
+        if not done:
+            lib.call("conv3x3", ptr(x), ptr(wc), ptr(y), ptr(bias), ptr(res), ptr(rowvec), B, H, W, C, Ho, Wo, N,
+                     9 * C, C, 1, stride, up, 0, 0, 0, dt(x), dt(y), stream())
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, wc)
         ctx.weight, ctx.bias = owner
         ctx.geom = (B, H, W, C, Ho, Wo, N, stride, up)
@@ -156,12 +207,23 @@ class Conv3x3Fn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dfull = torch.empty((B, H * up, W * up, C), dtype=dy.dtype, device=dy.device)
-            if stride == 2 and dy.dtype == torch.bfloat16 and H == 2 * Ho and W == 2 * Wo:
-                # tensor-core mode: zero-insert dy so the transposed conv is a plain stride-1 data gradient
+            def dgrad_s1(g, Hg, Wg):
+                """stride-1 data gradient of g [B,Hg,Wg,N] -> dfull (tensor cores: bf16, or fp32 as three bf16 passes)"""
+                if ctx.split:
+                    ws, n = _split_ws(g.numel(), wc.numel(), g.device)
+                    if lib.try_call("conv3x3_split3", ptr(g), ptr(wc), wc.numel(), ptr(dfull), None, None, None, B, Hg,
+                                    Wg, N, Hg, Wg, C, 1, C, 9 * C, 1, 1, ptr(ws), n, stream()):
+                        return
+                lib.call("conv3x3", ptr(g), ptr(wc), ptr(dfull), None, None, None, B, Hg, Wg, N, Hg, Wg, C,
+                         1, C, 9 * C, 1, 1, 0, 1, 0, dt(g), dt(dfull), stream())
+
+            if stride == 2 and (dy.dtype == torch.bfloat16 or ctx.split) and H == 2 * Ho and W == 2 * Wo:
+                # tensor-core modes: zero-insert dy so the transposed conv is a plain stride-1 data gradient
                 dyz = torch.empty((B, H, W, N), dtype=dy.dtype, device=dy.device)
                 lib.call("zero_insert2x", ptr(dy), ptr(dyz), B, Ho, Wo, N, dt(dy), stream())
-                lib.call("conv3x3", ptr(dyz), ptr(wc), ptr(dfull), None, None, None, B, H, W, N, H, W, C,
-                         1, C, 9 * C, 1, 1, 0, 1, 0, dt(dy), dt(dfull), stream())
+                dgrad_s1(dyz, H, W)
+            elif stride == 1 and up == 1:
+                dgrad_s1(dy, Ho, Wo)
             else:
                 lib.call("conv3x3", ptr(dy), ptr(wc), ptr(dfull), None, None, None, B, Ho, Wo, N, H * up, W * up, C,
                          1, C, 9 * C, stride, 1, 1 if stride > 1 else 0, 1, 0, dt(dy), dt(dfull), stream())
@@ -171,8 +233,14 @@ class Conv3x3Fn(Function):
             else:
                 dx = dfull
         if ctx.needs_input_grad[1]:
-            lib.call("conv3x3_wgrad", ptr(x), ptr(dy), ptr(_grad_of(ctx.weight)), B, H, W, C, Ho, Wo, N,
-                     9 * C, C, 1, stride, up, 1, dt(x), stream())
+            done = False
+            if ctx.split and up == 1:
+                ws, n = _split_ws(x.numel(), dy.numel(), x.device)
+                done = lib.try_call("conv3x3_wgrad_split3", ptr(x), ptr(dy), ptr(_grad_of(ctx.weight)), B, H, W, C, Ho, Wo,
+                                    N, 9 * C, C, 1, stride, ptr(ws), n, stream())
+            if not done:
+                lib.call("conv3x3_wgrad", ptr(x), ptr(dy), ptr(_grad_of(ctx.weight)), B, H, W, C, Ho, Wo, N,
+                         9 * C, C, 1, stride, up, 1, dt(x), stream())
         if ctx.bias is not None and ctx.needs_input_grad[3]:
             lib.call("colsum", ptr(dy), ptr(_grad_of(ctx.bias)), 1, B * Ho * Wo, N, 1, dt(dy), stream())
         drow = None
@@ -278,20 +346,20 @@ def _rows(t):
     return ld
 
 
-def _scores(q, k, b0, cb, heads, N, M, d, scale):
+def _scores(q, k, b0, cb, heads, N, M, d, scale, split=False):
     """P = softmax(scale Q K^T) for batch rows [b0, b0+cb): [cb, heads, N, Mp] with rows padded to Mp = ceil8(M)
     elements so the bf16 matrices are valid TMA operands of the batched tensor-core GEMMs (77 text keys -> 80)."""
     Mp = (M + 7) // 8 * 8
     lq, lk = _rows(q), _rows(k)
     S = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
     gemm(q[b0:], lq, 1, k[b0:], lk, 1, S, Mp, N, M, d, a_sb=(N * lq, d), b_sb=(M * lk, d), c_sb=(heads * N * Mp, N * Mp),
-         nb=(cb, heads), in_dtype=dt(q), out_dtype=F32)
+         nb=(cb, heads), in_dtype=dt(q), out_dtype=F32, split=split)
     P = S if q.dtype == torch.float32 else torch.empty(S.shape, dtype=q.dtype, device=q.device)
     lib.call("softmax_fwd", ptr(S), ptr(P), cb * heads * N, M, Mp, scale, dt(P), stream())
     return P, Mp
 
 
-def _attention_forward(q, k, v, heads, want_backward=True):
+def _attention_forward(q, k, v, heads, want_backward=True, split=False):
     """softmax(Q K^T / sqrt(d)) V per head; q [B,N,C], k/v [B,M,C] row-strided views, heads interleaved in C (head h =
     channels [h d, (h+1) d)).  Returns (o dense [B,N,C], saved-for-backward tuple, flash_bwd flag).
     bf16: tcgen05 flash attention (scores never reach HBM); fp32-exact path: fp32 scores materialised per batch
@@ -312,14 +380,14 @@ def _attention_forward(q, k, v, heads, want_backward=True):
     lv = _rows(v)
     for b0 in range(0, B, cbs):
         cb = min(cbs, B - b0)
-        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale)
+        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale, split)
         gemm(P, Mp, 1, v[b0:], 1, lv, o[b0:], C, N, d, M, a_sb=(heads * N * Mp, N * Mp), b_sb=(M * lv, d),
-             c_sb=(N * C, d), nb=(cb, heads))
+             c_sb=(N * C, d), nb=(cb, heads), split=split)
         del P
     return o, (), False
 
 
-def _attention_backward(q, k, v, extra, flash_bwd, do, heads, dq, dk, dv):
+def _attention_backward(q, k, v, extra, flash_bwd, do, heads, dq, dk, dv, split=False):
     """writes dq [B,N,C], dk/dv [B,M,C] (row-strided views, e.g. the thirds of one packed gradient tensor)."""
     B, N, C = q.shape
     M = k.shape[1]
@@ -338,19 +406,22 @@ def _attention_backward(q, k, v, extra, flash_bwd, do, heads, dq, dk, dv):
     lq, lk, lv, ldq, ldk, ldv = _rows(q), _rows(k), _rows(v), _rows(dq), _rows(dk), _rows(dv)
     for b0 in range(0, B, cbs):
         cb = min(cbs, B - b0)
-        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale)
+        P, Mp = _scores(q, k, b0, cb, heads, N, M, d, scale, split)
         pb = (heads * N * Mp, N * Mp)
         # dV[j, c] = sum_i P[i, j] dO[i, c]
-        gemm(P, 1, Mp, do[b0:], 1, C, dv[b0:], ldv, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * ldv, d), nb=(cb, heads))
+        gemm(P, 1, Mp, do[b0:], 1, C, dv[b0:], ldv, M, d, N, a_sb=pb, b_sb=(N * C, d), c_sb=(M * ldv, d), nb=(cb, heads),
+             split=split)
         # dP[i, j] = sum_c dO[i, c] V[j, c]
         dP = torch.empty((cb, heads, N, Mp), dtype=torch.float32, device=q.device)
         gemm(do[b0:], C, 1, v[b0:], lv, 1, dP, Mp, N, M, d, a_sb=(N * C, d), b_sb=(M * lv, d), c_sb=pb, nb=(cb, heads),
-             in_dtype=dt(q), out_dtype=F32)
+             in_dtype=dt(q), out_dtype=F32, split=split)
         dS = dP if q.dtype == torch.float32 else torch.empty(dP.shape, dtype=q.dtype, device=q.device)
         lib.call("softmax_bwd", ptr(P), ptr(dP), ptr(dS), cb * heads * N, M, Mp, scale, dt(dS), stream())
         # dQ[i, c] = sum_j dS[i, j] K[j, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]
-        gemm(dS, Mp, 1, k[b0:], 1, lk, dq[b0:], ldq, N, d, M, a_sb=pb, b_sb=(M * lk, d), c_sb=(N * ldq, d), nb=(cb, heads))
-        gemm(dS, 1, Mp, q[b0:], 1, lq, dk[b0:], ldk, M, d, N, a_sb=pb, b_sb=(N * lq, d), c_sb=(M * ldk, d), nb=(cb, heads))
+        gemm(dS, Mp, 1, k[b0:], 1, lk, dq[b0:], ldq, N, d, M, a_sb=pb, b_sb=(M * lk, d), c_sb=(N * ldq, d), nb=(cb, heads),
+             split=split)
+        gemm(dS, 1, Mp, q[b0:], 1, lq, dk[b0:], ldk, M, d, N, a_sb=pb, b_sb=(N * lq, d), c_sb=(M * ldk, d), nb=(cb, heads),
+             split=split)
         del P, dP, dS
 
 
@@ -360,7 +431,8 @@ class AttentionFn(Function):
     @staticmethod
     def forward(ctx, q, k, v, heads):
         q, k, v = _c(q), _c(k), _c(v)
-        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads)
+        ctx.split = _SPLIT[0]
+        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads, split=ctx.split)
         ctx.save_for_backward(q, k, v, *extra)
         ctx.heads = heads
         return o
@@ -369,7 +441,7 @@ class AttentionFn(Function):
     def backward(ctx, do):
         q, k, v, *extra = ctx.saved_tensors
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv)
+        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv, split=ctx.split)
         return dq, dk, dv, None
 
 
@@ -392,7 +464,8 @@ class PackedAttentionFn(Function):
         a = _c(a)
         b = _c(b) if b is not None else None
         q, k, v = PackedAttentionFn._split(a, b)
-        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads)
+        ctx.split = _SPLIT[0]
+        o, extra, ctx.flash_bwd = _attention_forward(q, k, v, heads, split=ctx.split)
         ctx.save_for_backward(a, b, *extra)
         ctx.heads = heads
         return o
@@ -404,7 +477,7 @@ class PackedAttentionFn(Function):
         da = torch.empty_like(a)
         db = torch.empty_like(b) if b is not None else None
         dq, dk, dv = PackedAttentionFn._split(da, db)
-        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv)
+        _attention_backward(q, k, v, extra, ctx.flash_bwd, do, ctx.heads, dq, dk, dv, split=ctx.split)
         return da, db, None
 
 

@@ -156,12 +156,17 @@ def save_network_snapshot(G_ema, fname):
     return fname
 
 
-def load_network_snapshot(fname, into=None, compute_dtype=torch.bfloat16, device=None):
-    """-> UNet2DConditionModel (or `into`, updated in place).  Accepts this module's snapshots and, where diffusers is
-    importable, the reference's `pickle.dump({'ema': module})` files."""
+def load_network_snapshot(fname, into=None, compute_dtype=torch.bfloat16, device=None, allow_pickle=False):
+    """-> UNet2DConditionModel (or `into`, updated in place).  Reads this module's tensor-only snapshots with
+    `weights_only=True`.  The reference's format - `pickle.dump({'ema': module})`, which is also what
+    training_loop() writes - is a pickle of a module object and executes code on load: it is read only with
+    `allow_pickle=True` (trusted files)."""
     try:
         data = torch.load(fname, map_location="cpu", weights_only=True)
-    except Exception:  # noqa: BLE001 - the reference's snapshots are plain pickles of module objects
+    except (pickle.UnpicklingError, RuntimeError) as e:
+        if not allow_pickle:
+            raise RuntimeError("%s is not a tensor-only snapshot; pass allow_pickle=True to unpickle a trusted "
+                               "{'ema': module} file (%s)" % (fname, type(e).__name__)) from e
         with open(fname, "rb") as f:
             data = pickle.load(f)
     ema = data["ema"]
@@ -232,9 +237,14 @@ def save_training_state(step, fname):
     return fname
 
 
-def load_training_state(step, fname):
+def load_training_state(step, fname, allow_pickle=False):
     """restores networks, Adam buckets and the image counter (sid_training_loop.py:296-310)."""
-    data = torch.load(fname, map_location="cpu", weights_only=False)
+    try:
+        data = torch.load(fname, map_location="cpu", weights_only=True)     # this module's own dumps: tensors + containers
+    except (pickle.UnpicklingError, RuntimeError):
+        if not allow_pickle:
+            raise
+        data = torch.load(fname, map_location="cpu", weights_only=False)    # the reference's dumps hold module objects
 
     def sd_of(x):
         return x.state_dict() if hasattr(x, "state_dict") and not isinstance(x, dict) else x

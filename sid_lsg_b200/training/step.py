@@ -4,14 +4,17 @@ Host orchestration of /root/reference/training/sid_training_loop.py:383-567; eve
 of libsidlsg.so.  Differences from the reference that do not change results:
   * NaN rows are zero-weighted inside the fused loss kernels instead of being filtered by shape (App. B-6);
   * nan_to_num + clip + Adam + EMA (+ bf16 shadow refresh) are ONE pass over the flat buckets;
-  * the data-parallel gradient mean is ONE NCCL allreduce per network per iteration on the flat gradient bucket
-    (the reference's DDP does the same reduction in 25 MiB buckets, :316-323), issued after the last
-    accumulation round (`ddp_sync` semantics, torch_utils/misc.py:168-175).
+  * the data-parallel gradient mean runs through ddp.FlatDDP: the trainable networks are wrapped exactly where the
+    reference wraps them in DistributedDataParallel (:316-323), every forward sits under `misc.ddp_sync(net, last
+    accumulation round)` like the reference's (:406, 416, 487, 494; torch_utils/misc.py:168-175), and the reduction of
+    each stage's gradient range starts inside backward (side stream) instead of in 25 MiB autograd buckets.
 """
 import torch
 import torch.distributed as dist
 
 from .. import ops
+from ..ddp import FlatDDP
+from ..torch_utils.misc import ddp_sync
 from .sid_sd_util import PromptBatch, sid_sd_sampler, sid_sd_denoise
 
 
@@ -27,6 +30,16 @@ def _world():
     return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
+def _val(m, key):
+    """a micro-batch entry, or a callable producing it when it is first needed (draws made in the reference's order:
+    the f_psi phase draws its timesteps AFTER the generator forward, :413)."""
+    v = m[key]
+    if callable(v):
+        v = v()
+        m[key] = v
+    return v
+
+
 class SiDLSGStep:
     """State + the two update phases.  `true_score`, `fake_score`, `G`, `G_ema` are UNet2DConditionModel
     instances with flat buckets (the reference builds them with deepcopy, :284-287, 327)."""
@@ -34,7 +47,7 @@ class SiDLSGStep:
     def __init__(self, true_score, fake_score, G, G_ema, scheduler, *, lr=1e-6, glr=1e-6, betas=(0.0, 0.999),
                  eps=1e-8, fp16=False, alpha=1.0, init_timestep=625, tmin=20, tmax=980, num_steps=1,
                  cfg_train_fake=1.0, cfg_eval_fake=1.0, cfg_eval_real=1.0, loss_scaling=1.0, loss_scaling_G=1.0,
-                 ema_halflife_kimg=50, ema_rampup_ratio=0.05):
+                 ema_halflife_kimg=50, ema_rampup_ratio=0.05, overlap_allreduce=True):
         self.true_score, self.fake_score, self.G, self.G_ema = true_score, fake_score, G, G_ema
         self.sched = scheduler
         self.lr, self.glr, self.betas, self.eps, self.fp16 = lr, glr, betas, eps, fp16
@@ -43,63 +56,86 @@ class SiDLSGStep:
         self.loss_scaling, self.loss_scaling_G = loss_scaling, loss_scaling_G
         self.ema_halflife_kimg, self.ema_rampup_ratio = ema_halflife_kimg, ema_rampup_ratio
         self.cur_nimg = 0
+        for net in (true_score, fake_score, G, G_ema):
+            if net is not None and net.flat is None:
+                net.flatten_()
         true_score.eval().requires_grad_(False)
-        if G_ema is not None:
+        if G_ema is not None and G_ema is not G:
             G_ema.eval().requires_grad_(False)
         fake_score.flat.init_adam(betas[0])
         G.flat.init_adam(betas[0])
+        # sid_training_loop.py:316-323 (parameters broadcast from rank 0, gradient mean on synchronised backwards)
+        self.fake_score_ddp = FlatDDP(fake_score, overlap=overlap_allreduce)
+        self.G_ddp = FlatDDP(G, overlap=overlap_allreduce)
+        if _world() > 1 and G_ema is not None and G_ema is not G:
+            G_ema.flat.copy_from(G.flat)
 
     # -- f_psi update: sid_training_loop.py:389-462 --------------------------------------------------------
-    def fake_score_phase(self, microbatches, batch_gpu_total=None):
-        """microbatches: list of dicts {z, noise, t, cond, uncond[, sub_noise]} (device tensors)."""
-        G, f = self.G, self.fake_score
+    def fake_score_phase(self, microbatches, batch_gpu_total=None, rounds=None):
+        """microbatches: iterable of dicts {z, noise, t, cond, uncond[, sub_noise]} (device tensors, or callables
+        evaluated at the point the reference makes the corresponding draw)."""
+        f = self.fake_score
         f.train().requires_grad_(True)
         f.flat.zero_grad()
-        total = batch_gpu_total or sum(m["z"].shape[0] for m in microbatches)
+        if rounds is None:
+            microbatches = list(microbatches)
+            rounds = len(microbatches)
+        total = batch_gpu_total or sum(_val(m, "z").shape[0] for m in microbatches)
         out = None
-        for m in microbatches:
-            b = m["z"].shape[0]
+        for r, m in enumerate(microbatches):
+            z = _val(m, "z")
+            noise = _val(m, "noise")
+            b = z.shape[0]
             prompts = PromptBatch(m["cond"], m["uncond"])
-            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=m["z"].device)
-            with torch.no_grad():
-                images = sid_sd_sampler(G, m["z"], prompts, init_t, self.sched, num_steps=self.num_steps,
+            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=z.device)
+            with ddp_sync(self.G_ddp, False), torch.no_grad():
+                images = sid_sd_sampler(self.G_ddp, z, prompts, init_t, self.sched, num_steps=self.num_steps,
                                         sub_noise=m.get("sub_noise"))
-            eps_hat = sid_sd_denoise(f, images, m["noise"], prompts, m["t"], self.sched, predict_x0=False,
-                                     guidance_scale=self.kappa1)
-            loss, out = ops.fake_loss(eps_hat, m["noise"], self.loss_scaling / total)
-            loss.backward()
+            t = _val(m, "t")
+            with ddp_sync(self.fake_score_ddp, r == rounds - 1):
+                eps_hat = sid_sd_denoise(self.fake_score_ddp, images, noise, prompts, t, self.sched, predict_x0=False,
+                                         guidance_scale=self.kappa1)
+                loss, out = ops.fake_loss(eps_hat, noise, self.loss_scaling / total)
+                loss.backward()
         f.eval().requires_grad_(False)
-        f.flat.allreduce_grad()
         f.flat.adam_step(self.lr, self.betas, self.eps, grad_scale=1.0 / _world())
         return out  # device float[2] {loss of the last micro-batch, valid rows}: no host sync here
 
     # -- G_theta update: sid_training_loop.py:468-549, EMA :553-565 -----------------------------------------
-    def generator_phase(self, microbatches, batch_gpu_total=None, batch_size=None, return_images=False):
-        G, f, phi = self.G, self.fake_score, self.true_score
+    def generator_phase(self, microbatches, batch_gpu_total=None, batch_size=None, return_images=False, rounds=None):
+        G, phi = self.G, self.true_score
         G.train().requires_grad_(True)
         G.flat.zero_grad()
-        total = batch_gpu_total or sum(m["z"].shape[0] for m in microbatches)
+        if rounds is None:
+            microbatches = list(microbatches)
+            rounds = len(microbatches)
+        total = batch_gpu_total or sum(_val(m, "z").shape[0] for m in microbatches)
         out = None
         imgs = []
-        for m in microbatches:
-            b = m["z"].shape[0]
+        for r, m in enumerate(microbatches):
+            z = _val(m, "z")
+            noise = _val(m, "noise")
+            t = _val(m, "t")
+            b = z.shape[0]
             prompts = PromptBatch(m["cond"], m["uncond"])
-            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=m["z"].device)
-            images = sid_sd_sampler(G, m["z"], prompts, init_t, self.sched, num_steps=self.num_steps,
-                                    sub_noise=m.get("sub_noise"))
-            y_fake = sid_sd_denoise(f, images, m["noise"], prompts, m["t"], self.sched, guidance_scale=self.kappa2)
-            y_real = sid_sd_denoise(phi, images, m["noise"], prompts, m["t"], self.sched, guidance_scale=self.kappa4)
-            loss, out = ops.lsg_loss(images, y_real, y_fake, self.alpha, self.loss_scaling_G / total)
-            loss.backward()
+            init_t = torch.full((b,), self.init_timestep, dtype=torch.long, device=z.device)
+            with ddp_sync(self.G_ddp, r == rounds - 1):
+                images = sid_sd_sampler(self.G_ddp, z, prompts, init_t, self.sched, num_steps=self.num_steps,
+                                        sub_noise=m.get("sub_noise"))
+                with ddp_sync(self.fake_score_ddp, False):
+                    y_fake = sid_sd_denoise(self.fake_score_ddp, images, noise, prompts, t, self.sched,
+                                            guidance_scale=self.kappa2)
+                    y_real = sid_sd_denoise(phi, images, noise, prompts, t, self.sched, guidance_scale=self.kappa4)
+                    loss, out = ops.lsg_loss(images, y_real, y_fake, self.alpha, self.loss_scaling_G / total)
+                    loss.backward()
             if return_images:
                 imgs.append(images.detach())
         G.eval().requires_grad_(False)
-        G.flat.allreduce_grad()
         world = _world()
         bs = batch_size or total * world
         beta = 0.0
         ema = None
-        if self.G_ema is not None and self.ema_halflife_kimg > 0:
+        if self.G_ema is not None and self.G_ema is not G and self.ema_halflife_kimg > 0:
             beta = ema_beta(bs, self.cur_nimg, self.ema_halflife_kimg, self.ema_rampup_ratio)
             ema = self.G_ema.flat
         G.flat.adam_step(self.glr, self.betas, self.eps, grad_scale=1.0 / world, clip=1.0 if self.fp16 else 0.0,
@@ -138,6 +174,23 @@ def synth_microbatch(b, cfg, seed, device, dropout=False, num_steps=1, tmin=20, 
     if device is None:
         return m
     return to_device(m, device)
+
+
+def device_microbatch(b, cfg, draws, dropout=False, uncond=None, tmin=20, tmax=980):
+    """Synthetic micro-batch drawn ON THE DEVICE from a training.draws.DrawStream (the reference's on-device z /
+    noise / t sampling, sid_training_loop.py:398-402, 413, 479-484, with synthetic prompt embeddings in place of the
+    text encoder): no host->device traffic at all."""
+    d = cfg.cross_attention_dim
+    hw = cfg.sample_size
+    if uncond is None:
+        uncond = draws.randn([1, 77, d])
+    uncond = uncond.expand(b, 77, d)
+    cond = draws.randn([b, 77, d])
+    if dropout:
+        drop = (draws.rand_cpu(b) < 0.1).to(cond.device)
+        cond = torch.where(drop[:, None, None], uncond, cond)
+    z = draws.randn([b, cfg.in_channels, hw, hw])
+    return dict(cond=cond, uncond=uncond, z=z, noise=draws.randn_like(z), t=draws.randint(tmin, tmax, (b,)))
 
 
 def to_device(m, device):

@@ -291,7 +291,8 @@ def test_adam_ema_matches_torch():
     lin.to(DEV)
     ema = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5)).to(DEV)
     ema.load_state_dict(lin.state_dict())
-    fp, fe = FlatParams(lin, shadow=True), FlatParams(ema)
+    fp, fe = FlatParams(lin, shadow=True), FlatParams(ema, shadow=True)
+    fp.ensure_grad()
     opt = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.0, 0.999), eps=1e-8)
     for it in range(3):
         grads = [torch.randn(p.shape, generator=g) for p in ref.parameters()]
@@ -309,6 +310,8 @@ def test_adam_ema_matches_torch():
         close(pd, p, rtol=1e-5, atol=1e-6, what="adam param")
         close(ed, e, rtol=1e-5, atol=1e-6, what="ema")
         close(pd._shadow, p.detach().bfloat16(), rtol=1e-2, atol=1e-2, what="bf16 shadow")
+        # the EMA network's bf16 shadow follows its master (a bf16 forward of G_ema must see the averaged weights)
+        assert torch.equal(ed._shadow, ed.detach().bfloat16()), "ema bf16 shadow is stale"
 
 
 def test_no_cpu_fallback():

@@ -90,7 +90,7 @@ def test_deepcopy_and_frozen_networks():
     x = torch.randn(1, 4, 16, 16, device=DEV, requires_grad=True)
     e = torch.randn(1, 77, cfg.cross_attention_dim, device=DEV)
     m2(x, torch.tensor([5], device=DEV), encoder_hidden_states=e).sample.sum().backward()
-    assert x.grad is not None and float(m2.flat.grad.abs().max()) == 0.0  # dgrad only, no wgrad into a frozen net
+    assert x.grad is not None and m2.flat.grad is None  # dgrad only: a frozen net never allocates its gradient bucket
 
 
 def _to_dev(mbs):
