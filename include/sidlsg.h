@@ -180,6 +180,16 @@ int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, v
                      float ema_beta, float weight_decay, void* stream);
 int sidlsg_ema_update(const float* p, float* ema, long n, float beta, void* stream);
 
+/* development aid: attention forward (d <= 64) with in-kernel clock64 stamps (32 x 16 long long, device memory) */
+int sidlsg_debug_attention_fwd_trace(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                                     int N, int M, int H, int d, long ldq, long ldk, long ldv, void* trace,
+                                     void* stream);
+/* development aid: attention backward with in-kernel clock64 stamps (32 x 16 long long, device memory) */
+int sidlsg_debug_attention_bwd_trace(const void* q, const void* k, const void* v, const void* o,
+                                     const void* dout, const float* lse, float* delta, float* dq_acc, void* dq,
+                                     void* dk, void* dv, int B, int N, int M, int H, int d, long ldq, long ldk,
+                                     long ldv, long lddq, long lddk, long lddv, void* trace, void* stream);
+
 /* ---- fp32-accurate tensor-core mode (csrc/split3.cu) --------------------------------------------------------
  * The same contractions for fp32 operands and fp32 outputs, computed on tcgen05 as three bf16 passes
  * (A_hi B_hi + A_hi B_lo + A_lo B_hi, fp32 accumulation): the parity instrument for the reference's fp32 / TF32-off

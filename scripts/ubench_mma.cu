@@ -10,9 +10,9 @@
 
 using namespace sidlsg;
 
-struct MmaCfg { int N, nacc, a_tmem, reps, tcols; };
+struct MmaCfg { int N, nacc, a_tmem, reps, tcols, a_mn, b_mn; };
 
-template <bool ELECT>
+template <bool ELECT_UNUSED>
 __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCfg c) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCf
   tc_fence_after();
   const uint32_t tmem = *slot_ptr;
   if (warp == 0) {
-   if (role_leader<ELECT>(lane)) {
-    const uint32_t idesc = make_idesc(c.N, 0, 0);
+   if (role_leader()) {
+    const uint32_t idesc = make_idesc(c.N, c.a_mn, c.b_mn);
     const uint32_t a_t = tmem + c.nacc * c.N;            // A-in-TMEM region behind the accumulators (32 columns = K 64)
     const long long t0 = clock64();
     int i = 0;
@@ -37,9 +37,11 @@ __global__ void __launch_bounds__(128, 2) mma_issue_kernel(long long* out, MmaCf
 #pragma unroll
       for (int k = 0; k < 4; ++k, ++i) {
         const uint32_t d = tmem + (i % c.nacc) * c.N;
-        const uint64_t bd = make_desc(b_smem + k * 32, 1024, 0);
+        // K-major: +32 B per 16-element K step; MN-major: 64-wide MN atoms 16 KB apart, +2048 B per 16-row K step
+        const uint64_t bd = c.b_mn ? make_desc(b_smem + k * 2048, 1024, 16384) : make_desc(b_smem + k * 32, 1024, 0);
+        const uint64_t ad = c.a_mn ? make_desc(a_smem + k * 2048, 1024, 16384) : make_desc(a_smem + k * 32, 1024, 0);
         if (c.a_tmem) tc_mma_bf16_ta(d, a_t + k * 8, bd, idesc, 1);
-        else tc_mma_bf16(d, make_desc(a_smem + k * 32, 1024, 0), bd, idesc, 1);
+        else tc_mma_bf16(d, ad, bd, idesc, 1);
       }
     }
     const long long t1 = clock64();
@@ -70,7 +72,7 @@ static int sweep(long long* out, int smem) {
         for (int nacc : {1, 2, 4}) {
           const int tcols = ctas == 2 ? 256 : 512;
           if (nacc * N + 32 > tcols) continue;
-          MmaCfg c{N, nacc, a_tmem, 256, tcols};
+          MmaCfg c{N, nacc, a_tmem, 256, tcols, 0, 0};
           long long h[2 * 296];
           for (int rep = 0; rep < 2; ++rep) {
             mma_issue_kernel<ELECT><<<148 * ctas, 128, smem>>>(out, c);
@@ -86,10 +88,38 @@ static int sweep(long long* out, int smem) {
   return 0;
 }
 
-int main() {
+// operand majorness (the attention backward feeds dV / dK / dQ with MN-major operands: the same Q / dO / K / dS^T tiles
+// re-read transposed): cycles per MMA, one CTA per SM, elect.sync issue
+static int sweep_major(long long* out, int smem) {
+  cudaFuncSetAttribute(mma_issue_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  printf("---- operand majorness (A smem unless TMEM), 1 CTA/SM, elect.sync\n");
+  printf("%4s %6s %6s %6s | %10s %12s\n", "N", "A", "a_maj", "b_maj", "issue", "issue+drain");
+  for (int N : {48, 64, 128})
+    for (int a_tmem = 0; a_tmem <= 1; ++a_tmem)
+      for (int a_mn = 0; a_mn <= (a_tmem ? 0 : 1); ++a_mn)
+        for (int b_mn = 0; b_mn <= 1; ++b_mn) {
+          MmaCfg c{N, 1, a_tmem, 256, 512, a_mn, b_mn};
+          long long h[2 * 148];
+          for (int rep = 0; rep < 2; ++rep) {
+            mma_issue_kernel<true><<<148, 128, smem>>>(out, c);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          }
+          cudaMemcpy(h, out, sizeof(long long) * 2 * 148, cudaMemcpyDeviceToHost);
+          double iss = 0, tot = 0;
+          for (int i = 0; i < 148; ++i) { iss += (double)h[2 * i]; tot += (double)h[2 * i + 1]; }
+          const double n = 148.0 * c.reps * 4;
+          printf("%4d %6s %6s %6s | %10.1f %12.1f\n", N, a_tmem ? "TMEM" : "smem", a_mn ? "MN" : "K", b_mn ? "MN" : "K", iss / n, tot / n);
+        }
+  return 0;
+}
+
+int main(int argc, char** argv) {
   long long* out;
   cudaMalloc(&out, 2 * 296 * sizeof(long long));
   const int smem = 16384 + 32768 + 1024 + 64;
+  if (argc > 1 && argv[1][0] == 'm') return sweep_major(out, smem);
   if (sweep<true>(out, smem)) return 1;
-  return sweep<false>(out, smem);
+  if (sweep_major(out, smem)) return 1;
+  return 0;
 }

@@ -30,6 +30,7 @@ struct AttnParams {
   bf16* o;
   float* lse;
   unsigned wait_hint;    // ns, helper-warp mbarrier waits (tc_wait_hint_ns)
+  long long* trace;      // attn_fwd3_kernel<true> only: clock64 stamps of CTA (1,0,0), 16 slots per key tile
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -346,6 +347,279 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, two query tiles per CTA (d <= 64: the N = 4096, d = 40 layers of SD1.5 that hold 3/4 of all attention time, and
+// every SD2.1 layer).  Measured on B200 with elect.sync issue (profiles/r02_ubench_mma_issue_b200.txt): per 128 x 128
+// tile the tensor pipe needs 3 x 109 clk for S = Q K^T and 8 x 55 clk for O += P V when P is the TMEM A operand (8 x 81
+// from shared memory), the MUFU pipe 1037 clk for the exponentials - the single-tile kernel above runs them strictly one
+// after the other (2150 clk per tile).  Here ONE CTA per SM owns TWO 128-row query tiles A, B with their own S, O and P
+// regions in TMEM (S 2 x 128 | O 2 x 64 | P 2 x 64 columns = 512) and their own 4 softmax warps; the single MMA warp
+// alternates  P_A V -> Q_A K'^T -> P_B V -> Q_B K'^T,  so the exponentials of one tile run under the MMAs of the other
+// (FlashAttention-4's ping-pong schedule).  P never touches shared memory (tcgen05.st, bf16 pairs per 32-bit column),
+// K and V travel through separate TMA rings (K_{j+1} is needed while V_j is still in use).
+//   barriers: q_full[2], s_full[2] (MMA -> softmax), p_full[2] (softmax -> MMA, 4 warp arrivals), o_full[2] (P_X V retired),
+//             k_full / k_empty [KST], v_full / v_empty [VST]
+constexpr int A3_THREADS = 320;
+constexpr int A3_KST = 4, A3_VST = 4;
+
+template <bool TRACE>
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t q_smem = smem_base;                          // 2 x 16 KB
+  const uint32_t k_smem = q_smem + 2 * AT_CHUNK;              // A3_KST x 16 KB
+  const uint32_t v_smem = k_smem + A3_KST * AT_CHUNK;         // A3_VST x 16 KB
+  const uint32_t bar_base = v_smem + A3_VST * AT_CHUNK;
+  auto q_full = [&](int x) { return bar_base + 8u * x; };
+  auto s_full = [&](int x) { return bar_base + 16 + 8u * x; };
+  auto p_full = [&](int x) { return bar_base + 32 + 8u * x; };
+  auto o_full = [&](int x) { return bar_base + 48 + 8u * x; };
+  auto k_full = [&](int s) { return bar_base + 64 + 8u * s; };
+  auto k_empty = [&](int s) { return bar_base + 96 + 8u * s; };
+  auto v_full = [&](int s) { return bar_base + 128 + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 160 + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 192;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * AT_BQ), h = blockIdx.y, b = blockIdx.z;
+  const int T = (p.M + AT_BKV - 1) / AT_BKV;
+  const int ntile = (q0 + AT_BQ < p.N) ? 2 : 1;               // the second query tile may lie entirely past N
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) { printf("sidlsg attention: dynamic smem not 1024-aligned\n"); __trap(); }
+    for (int x = 0; x < 2; ++x) { mbar_init(q_full(x), 1); mbar_init(s_full(x), 1); mbar_init(p_full(x), 4); mbar_init(o_full(x), 1); }
+    for (int s2 = 0; s2 < 4; ++s2) { mbar_init(k_full(s2), 1); mbar_init(k_empty(s2), 1); mbar_init(v_full(s2), 1); mbar_init(v_empty(s2), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  auto s_tmem = [&](int x) { return tmem_base + 128u * x; };
+  auto o_tmem = [&](int x) { return tmem_base + 256u + 64u * x; };
+  auto p_tmem = [&](int x) { return tmem_base + 384u + 64u * x; };
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (role_leader()) {
+      for (int x = 0; x < ntile; ++x) {
+        mbar_expect_tx(q_full(x), AT_CHUNK);
+        tma_load_4d(&tmQ, q_full(x), q_smem + x * AT_CHUNK, 0, h, q0 + x * AT_BQ, b);
+      }
+      for (int j = 0; j < T; ++j) {
+        const int ks = j % A3_KST, vs = j % A3_VST;
+        mbar_wait_h(p.wait_hint, k_empty(ks), ((j / A3_KST) & 1) ^ 1);
+        mbar_expect_tx(k_full(ks), AT_CHUNK);
+        tma_load_4d(&tmK, k_full(ks), k_smem + ks * AT_CHUNK, 0, h, j * AT_BKV, b);
+        mbar_wait_h(p.wait_hint, v_empty(vs), ((j / A3_VST) & 1) ^ 1);
+        mbar_expect_tx(v_full(vs), AT_CHUNK);
+        tma_load_4d(&tmV, v_full(vs), v_smem + vs * AT_CHUNK, 0, h, j * AT_BKV, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (role_leader()) {
+      const int dsteps = p.dpad >> 4;
+      const uint32_t idesc_pv = make_idesc(p.dpad, 0, 1);
+      auto issue_qk = [&](int x, int j) {
+        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+        const uint32_t idesc = make_idesc((n_valid + 15) & ~15, 0, 0);
+        const uint32_t kb = k_smem + (j % A3_KST) * AT_CHUNK, qb = q_smem + x * AT_CHUNK;
+        for (int s2 = 0; s2 < dsteps; ++s2)
+          tc_mma_bf16(s_tmem(x), make_desc(qb + s2 * 32, 1024, 0), make_desc(kb + s2 * 32, 1024, 0), idesc, s2 > 0);
+        tc_commit(s_full(x));
+      };
+      for (int x = 0; x < ntile; ++x) mbar_wait_h(p.wait_hint, q_full(x), 0);
+      mbar_wait_h(p.wait_hint, k_full(0), 0);
+      tc_fence_after();
+      for (int x = 0; x < ntile; ++x) issue_qk(x, 0);
+      tc_commit(k_empty(0));
+      for (int j = 0; j < T; ++j) {
+        const int vs = j % A3_VST;
+        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+        const int ksteps = (n_valid + 15) >> 4;
+        const uint32_t vb = v_smem + vs * AT_CHUNK;
+        const bool more = j + 1 < T;
+        const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
+        mbar_wait_h(p.wait_hint, v_full(vs), (j / A3_VST) & 1);
+        if (more) mbar_wait_h(p.wait_hint, k_full((j + 1) % A3_KST), ((j + 1) / A3_KST) & 1);
+        for (int x = 0; x < ntile; ++x) {
+          if (tr) p.trace[j * 16 + 8 + 3 * x] = clock64();
+          mbar_wait_h(p.wait_hint, p_full(x), j & 1);
+          if (tr) p.trace[j * 16 + 9 + 3 * x] = clock64();
+          tc_fence_after();
+          for (int s2 = 0; s2 < ksteps; ++s2)
+            tc_mma_bf16_ta(o_tmem(x), p_tmem(x) + s2 * 8, make_desc(vb + s2 * 2048, 1024, AT_CHUNK), idesc_pv,
+                           (j > 0 || s2 > 0) ? 1u : 0u);
+          tc_commit(o_full(x));
+          if (more) issue_qk(x, j + 1);
+          if (tr) p.trace[j * 16 + 10 + 3 * x] = clock64();
+        }
+        tc_commit(v_empty(vs));
+        if (more) tc_commit(k_empty((j + 1) % A3_KST));
+      }
+    }
+  } else if ((warp >> 2) < ntile) {
+    // ===================== softmax / output: warps 0-3 own tile A, warps 4-7 tile B =====================
+    const int x = warp >> 2, wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;       // a warp reaches TMEM lanes 32 (warp % 4) .. + 31
+    const uint32_t st = s_tmem(x) + lane_off, ot = o_tmem(x) + lane_off, pt = p_tmem(x) + lane_off;
+    const float c = p.scale_log2;
+    const uint64_t c2 = pack2(c, c);
+    float m_used = -INFINITY, l_run = 0.f;
+
+    auto tile_max = [&](int n_valid) {
+      float mx = -INFINITY;
+      for (int cc = 0; cc < n_valid; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32_nowait(st + cc, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (cc + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      return mx;
+    };
+    // P = exp2(s*c - m*c) -> bf16 pairs in TMEM; returns the row sum, tracks the raw row max in mx
+    auto tile_exp = [&](int n_valid, float m, float& mx) {
+      const float nmc = -m * c;
+      const uint64_t nmc2 = pack2(nmc, nmc);
+      float ls = 0.f;
+      if (n_valid == AT_BKV) {
+        uint64_t ls2 = pack2(0.f, 0.f);
+#pragma unroll
+        for (int cc = 0; cc < AT_BKV; cc += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld32_nowait(st + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            mx = fmaxf(fmaxf(mx, x0), x1);
+            float t0, t1;
+            unpack2(ffma2(pack2(x0, x1), c2, nmc2), t0, t1);
+            const float p0 = ex2f(t0), p1 = ex2f(t1);
+            ls2 = fadd2(ls2, pack2(p0, p1));
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(pt + (cc >> 1), pk);
+        }
+        float a0, a1;
+        unpack2(ls2, a0, a1);
+        ls = a0 + a1;
+      } else {
+        for (int cc = 0; cc < n_valid; cc += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld32_nowait(st + cc, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const bool v0 = cc + i < n_valid, v1 = cc + i + 1 < n_valid;
+            const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            if (v0) mx = fmaxf(mx, x0);
+            if (v1) mx = fmaxf(mx, x1);
+            const float p0 = v0 ? ex2f(fmaf(x0, c, nmc)) : 0.f;
+            const float p1 = v1 ? ex2f(fmaf(x1, c, nmc)) : 0.f;
+            ls += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(pt + (cc >> 1), pk);
+        }
+      }
+      tmem_wait_st();
+      return ls;
+    };
+    auto rescale_o = [&](float f) {
+      for (int cc = 0; cc < p.dpad; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(ot + cc, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+        tmem_st16(ot + cc, r);
+      }
+      tmem_wait_st();
+    };
+
+    for (int j = 0; j < T; ++j) {
+      const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
+      const bool spec = j > 0 && n_valid == AT_BKV;
+      // s_full(j) is committed AFTER P_X V_{j-1} was issued, so its arrival also means that product has retired:
+      // O_X and the P_X region are ours again (no separate o_full wait on the critical path)
+      const bool tr = TRACE && (threadIdx.x & 127) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
+      if (tr) p.trace[j * 16 + 4 * x] = clock64();
+      mbar_wait(s_full(x), j & 1);
+      if (tr) p.trace[j * 16 + 4 * x + 1] = clock64();
+      tc_fence_after();
+      if (!spec) {
+        const float m_new = fmaxf(m_used, tile_max(n_valid));
+        const bool need = (m_new - m_used) * c > 8.f;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+          rescale_o(f);
+          l_run *= f;
+        }
+        if (need) m_used = m_new;
+      }
+      float mx = -INFINITY;
+      float l_tile = tile_exp(n_valid, m_used, mx);
+      if (spec) {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) * c > 8.f;
+        if (__any_sync(0xffffffffu, need)) {       // rare: this tile raised the max by more than 2^8 -> redo it
+          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+          rescale_o(f);
+          l_run *= f;
+          if (need) m_used = m_new;
+          l_tile = tile_exp(n_valid, m_used, mx);
+        }
+      }
+      l_run += l_tile;
+      if (tr) p.trace[j * 16 + 4 * x + 2] = clock64();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(x));
+    }
+    mbar_wait(o_full(x), (T - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + x * AT_BQ + row;
+    const float inv = 1.f / l_run;
+    const int C = p.H * p.d;
+    bf16* orow = p.o + ((long)b * p.N + q) * C + h * p.d;
+    for (int cc = 0; cc < p.dpad; cc += 16) {
+      uint32_t r[16];
+      tmem_ld16_nowait(ot + cc, r);
+      tmem_wait_ld();
+      if (q < p.N) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (cc + 8 * hh < p.d) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[8 * hh + 0]) * inv, __uint_as_float(r[8 * hh + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(r[8 * hh + 2]) * inv, __uint_as_float(r[8 * hh + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(r[8 * hh + 4]) * inv, __uint_as_float(r[8 * hh + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(r[8 * hh + 6]) * inv, __uint_as_float(r[8 * hh + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + cc + 8 * hh) = o;
+          }
+        }
+      }
+    }
+    if (q < p.N && p.lse) p.lse[((long)b * p.H + h) * p.N + q] = m_used * p.scale + logf(l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // head-sliced view of a [B, len, >= H*d] bf16 tensor with row stride ld elements (ld = H*d when dense; 3*H*d for
 // the q/k/v thirds of a packed projection output): dims (d, H, len, B)
 static bool make_head_map(CUtensorMap* m, const void* base, int d, int H, int len, int B, long ld, int rows = 128) {
@@ -364,8 +638,8 @@ using namespace sidlsg;
 // q [B,N,H*d], k/v [B,M,H*d] bf16 with row strides ldq/ldk/ldv elements (batch stride = rows * ld; multiples of 8);
 // o [B,N,H*d] bf16 dense; lse [B,H,N] fp32 (natural log, may be null).
 // Returns SIDLSG_ERR_UNSUPPORTED when the tensor-core path cannot take the shape (caller uses the fp32-exact path).
-extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
-                                    int M, int H, int d, long ldq, long ldk, long ldv, void* stream) {
+static int attention_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
+                              int M, int H, int d, long ldq, long ldk, long ldv, long long* trace, void* stream) {
   if (!tc_enabled()) { set_error("attention_fwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
   if (d % 8 || d < 16 || d > 192 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
     set_error("attention_fwd: unsupported shape B=%d N=%d M=%d H=%d d=%d", B, N, M, H, d);
@@ -386,10 +660,27 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = (bf16*)o; p.lse = lse;
   p.wait_hint = tc_wait_hint_ns();
+  p.trace = trace;
   CUtensorMap tq, tk, tv;
   if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
       !make_head_map(&tv, v, d, H, M, B, ldv))
     return SIDLSG_ERR_CUDA;
+  // d <= 64: two query tiles per CTA (attn_fwd3_kernel); SIDLSG_ATTN_FWD3=0 keeps the single-tile kernel (A/B switch)
+  static int fwd3 = -1;
+  if (fwd3 < 0) { const char* e = getenv("SIDLSG_ATTN_FWD3"); fwd3 = (e && e[0] == '0') ? 0 : 1; }
+  if (fwd3 && p.dpad <= 64) {
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(attn_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr3 = true;
+    }
+    const int smem3 = (2 + A3_KST + A3_VST) * AT_CHUNK + 256;
+    dim3 grid3((N + 2 * AT_BQ - 1) / (2 * AT_BQ), H, B);
+    if (trace) attn_fwd3_kernel<true><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    else attn_fwd3_kernel<false><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    return check_launch("attention_fwd");
+  }
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
   if (!g_attn_attr_done) {
     cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -400,6 +691,18 @@ extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v,
   if (p.dpad <= 128) attn_fwd_kernel<256><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   else attn_fwd_kernel<512><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   return check_launch("attention_fwd");
+}
+
+extern "C" int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int N,
+                                    int M, int H, int d, long ldq, long ldk, long ldv, void* stream) {
+  return attention_fwd_impl(q, k, v, o, lse, B, N, M, H, d, ldq, ldk, ldv, nullptr, stream);
+}
+
+// Development aid: forward (d <= 64 kernel) with in-kernel clock64 stamps of CTA (1,0,0); not used by the product path.
+extern "C" int sidlsg_debug_attention_fwd_trace(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                                                int N, int M, int H, int d, long ldq, long ldk, long ldv, void* trace,
+                                                void* stream) {
+  return attention_fwd_impl(q, k, v, o, lse, B, N, M, H, d, ldq, ldk, ldv, (long long*)trace, stream);
 }
 
 // =====================================================================================================================
@@ -431,8 +734,10 @@ struct AttnBwdParams {
   bf16* dk;
   bf16* dv;
   long lddk, lddv;       // row strides (elements) of dk / dv
+  long long* trace;      // TRACE instantiation only: clock64 stamps of CTA (1,0,0), 16 slots per query tile
 };
 
+template <bool TRACE>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -543,7 +848,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           issue_s(i + 1);
         }
+        const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
+        if (tr) p.trace[i * 16 + 8] = clock64();
         mbar_wait_h(p.wait_hint, pds_full, i & 1);
+        if (tr) p.trace[i * 16 + 9] = clock64();
         tc_fence_after();
         for (int s = 0; s < 8; ++s) {      // reduction over the 128 query rows of this tile
           const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
@@ -561,6 +869,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tc_commit(qdo_empty(st));
         tc_commit(dq_full);
+        if (tr) p.trace[i * 16 + 10] = clock64();
         if (i + 1 < TQ) {
           if (!early) {
             mbar_wait_h(p.wait_hint, qdo_full((i + 1) % QST), ((i + 1) / QST) & 1);
@@ -589,6 +898,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // drain dQ_i (TMEM lane = query row): stage the fp32 tile in smem, then ONE thread hands it to the TMA unit
       // as a bulk reduce-add into dq_acc (the partials of the K/V tiles meet in L2, no per-thread atomics)
       mbar_wait(dq_full, it & 1);
+      if (TRACE && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && it + 1 < 32) p.trace[(it + 1) * 16 + 2] = clock64();
       tc_fence_after();
       if (tid == 0) tma_wait_group_read0();        // the previous reduce has finished reading the staging tile
       named_bar_sync(2, 256);
@@ -630,7 +940,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float* ndl = sb + 128 + wg * 64;
       uint64_t ps2[32];                      // P * scale for this thread's 64 query columns (fp32 pairs)
       uint32_t pk[32];                       // P as packed bf16 pairs, stored once the previous tile's MMAs retired
+      const bool tr = TRACE && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
+      if (tr) p.trace[i * 16 + 0] = clock64();
       mbar_wait(s_full, i & 1);
+      if (tr) p.trace[i * 16 + 1] = clock64();
       tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -657,7 +970,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sread);     // S^T may be overwritten by the next tile's MMA
+      if (tr) p.trace[i * 16 + 3] = clock64();   // exponentials done (slot 2 = dq_full of tile i-1 seen, inside drain_dq)
       if (i > 0) drain_dq(i - 1);            // waits for tile i-1's MMAs: P^T / dS^T tiles and dQ are ours again
+      if (tr) p.trace[i * 16 + 4] = clock64();
       // publish the next tile's statistics (buffer (i+1)&1 was last read during tile i-1) and fetch tile i+2's
       stat[((i + 1) & 1) * 256 + tid] = stat_value(stat_next);
       stat_next = load_stat(i + 2);
@@ -667,7 +982,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int qd = 0; qd < 4; ++qd)
           st_shared_v4(p_row + wg * AT_CHUNK + (((half * 4 + qd) ^ rx) << 4), pk[half * 16 + 4 * qd],
                        pk[half * 16 + 4 * qd + 1], pk[half * 16 + 4 * qd + 2], pk[half * 16 + 4 * qd + 3]);
+      if (tr) p.trace[i * 16 + 5] = clock64();
       mbar_wait(dp_full, i & 1);
+      if (tr) p.trace[i * 16 + 6] = clock64();
       tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -697,6 +1014,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (tr) p.trace[i * 16 + 7] = clock64();
       named_bar_sync(1, 256);                 // statistics of tile i+1 are visible to every compute warp
     }
     drain_dq(TQ - 1);
@@ -793,10 +1111,10 @@ static bool g_attn_bwd_attr_done = false;
 // dq_acc: fp32 [B,N,H*d] scratch (zeroed here), delta: fp32 [B,H,N] scratch.  dq/dk/dv bf16 outputs.
 // q/k/v and dq/dk/dv may be column slices of packed tensors: ld* = their row strides in elements (o, dout dense).
 // Supports d % 8 == 0, 16 <= d <= 80 (TMEM: 256 + 3*dpad <= 512 columns); returns SIDLSG_ERR_UNSUPPORTED otherwise.
-extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
-                                    const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
-                                    int B, int N, int M, int H, int d, long ldq, long ldk, long ldv, long lddq,
-                                    long lddk, long lddv, void* stream) {
+static int attention_bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                              const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
+                              int B, int N, int M, int H, int d, long ldq, long ldk, long ldv, long lddq,
+                              long lddk, long lddv, long long* trace, void* stream) {
   if (!tc_enabled()) { set_error("attention_bwd: tcgen05 path unavailable on this device"); return SIDLSG_ERR_UNSUPPORTED; }
   const int dpad = (d + 15) & ~15;
   if (d % 8 || d < 16 || 256 + 3 * dpad > 512 || B <= 0 || N <= 0 || M <= 0 || H <= 0 || H > 65535 || B > 65535) {
@@ -833,6 +1151,7 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   p.lddk = lddk; p.lddv = lddv;
   p.stage_alias = d > 64;
   p.wait_hint = tc_wait_hint_ns();
+  p.trace = trace;
   CUtensorMap tq, tk, tv, tdo, tdq;
   if (!make_head_map(&tq, q, d, H, N, B, ldq) || !make_head_map(&tk, k, d, H, M, B, ldk) ||
       !make_head_map(&tv, v, d, H, M, B, ldv) || !make_head_map(&tdo, dout, d, H, N, B, (long)H * d))
@@ -847,11 +1166,13 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
   const int smem = (2 + 2 * p.q_stages) * p.dchunks * AT_CHUNK + 4 * AT_CHUNK + 2048 + 256 +
                    (p.stage_alias ? 0 : ((d + 31) / 32) * AT_CHUNK);
   if (!g_attn_bwd_attr_done) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_attn_bwd_attr_done = true;
   }
   dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
-  attn_bwd_kernel<<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  if (trace) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  else attn_bwd_kernel<false><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;
   // dq (bf16) = dq_acc (fp32)
@@ -861,4 +1182,22 @@ extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v,
     attn_dq_cast_kernel<<<(unsigned)((rows * (C >> 3) + 255) / 256), 256, 0, st>>>(dq_acc, (bf16*)dq, rows, C, lddq);
   }
   return check_launch("attention_bwd dq cast");
+}
+
+extern "C" int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                    const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
+                                    int B, int N, int M, int H, int d, long ldq, long ldk, long ldv, long lddq,
+                                    long lddk, long lddv, void* stream) {
+  return attention_bwd_impl(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, N, M, H, d, ldq, ldk, ldv, lddq, lddk,
+                            lddv, nullptr, stream);
+}
+
+// Development aid: the same backward with in-kernel clock64 stamps of CTA (1,0,0) written to `trace` (device memory,
+// 32 tiles x 16 slots of long long; see attn_bwd_kernel<true>).  Not used by the product path.
+extern "C" int sidlsg_debug_attention_bwd_trace(const void* q, const void* k, const void* v, const void* o,
+                                                const void* dout, const float* lse, float* delta, float* dq_acc, void* dq,
+                                                void* dk, void* dv, int B, int N, int M, int H, int d, long ldq, long ldk,
+                                                long ldv, long lddq, long lddk, long lddv, void* trace, void* stream) {
+  return attention_bwd_impl(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, N, M, H, d, ldq, ldk, ldv, lddq, lddk,
+                            lddv, (long long*)trace, stream);
 }

@@ -81,4 +81,7 @@ def test_full_size_iteration_matches_oracle(cfg_name, kappa):
         # loss_G is a signed sum of products of small score differences divided by w = mean|x_g - y_real|: it amplifies
         # relative UNet error by |terms| / |sum|; hold it to 2x the latent/loss tolerance plus an absolute floor
         assert abs(lg - lg_ref) <= 2 * tol_loss * abs(lg_ref) + tol_loss, (mode, lg, lg_ref, r)
-        assert r["update"] < (0.05 if dtype == torch.float32 else 0.6), (mode, r)
+        # Adam(beta1 = 0)'s first step moves every weight by ~lr * sign(g): the update's relative L2 error is
+        # 2 sqrt(fraction of flipped signs).  fp32: rounding-noise gradients only (<= 5 %); bf16: reported, and bounded
+        # by 1.0 (= a quarter of the signs), since weights with |g| below bf16 noise have no defined sign
+        assert r["update"] < (0.05 if dtype == torch.float32 else 1.0), (mode, r)
