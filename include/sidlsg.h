@@ -113,7 +113,7 @@ int sidlsg_attention_fwd(const void* q, const void* k, const void* v, void* o, f
                          int M, int H, int d, long ldq, long ldk, long ldv, void* stream);
 
 /* Backward of the above with the scores recomputed on the tensor cores: dq [B,N,H*d], dk/dv [B,M,H*d] bf16.
- * delta: fp32 [B,H,N] scratch (= sum_c o*dout, computed here); dq_acc: fp32 [B,N,H*d] scratch (zeroed here; dQ
+ * delta: fp32 [2,B,H,N] scratch (sum_c o*dout and -lse*log2(e), computed here); dq_acc: fp32 [B,N,H*d] scratch (zeroed here; dQ
  * partials of the K/V tiles are reduced into it with red.global.add).  d % 8 == 0, 16 <= d <= 80.
  * ld*: row strides (elements) of q/k/v and of the dq/dk/dv outputs (slices of packed tensors allowed). */
 int sidlsg_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,

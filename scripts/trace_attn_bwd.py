@@ -13,7 +13,7 @@ o = torch.empty_like(q)
 lse = torch.empty(B, H, N, device=dev, dtype=torch.float32)
 lib.call("attention_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, N, N, H, d, C, C, C, stream())
 do = torch.randn_like(o)
-delta = torch.empty_like(lse)
+delta = torch.empty((2,) + tuple(lse.shape), device=dev, dtype=torch.float32)
 dq_acc = torch.empty(B, N, C, device=dev, dtype=torch.float32)
 dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
 trace = torch.zeros(32 * 16, device=dev, dtype=torch.int64)
@@ -22,10 +22,13 @@ for _ in range(2):
              ptr(dq), ptr(dk), ptr(dv), B, N, N, H, d, C, C, C, C, C, C, ptr(trace), stream())
 torch.cuda.synchronize()
 t = trace.cpu().view(32, 16)
-names = ["c:loop_top", "c:s_full", "c:dq_full(i-1)", "c:exp_done", "c:drain_done", "c:P_stored", "c:dp_full", "c:ds_done",
-         "m:wait_pds", "m:pds_full", "m:issued"]
+names = {0: "c:top", 1: "c:s_full", 2: "c:P_done", 3: "c:dp_full", 4: "c:dS_done", 6: "d:dq_full", 7: "d:reduced",
+         8: "m:top", 9: "m:p_full", 10: "m:dV,S+", 11: "m:ds_full", 12: "m:dK", 13: "m:dq_empty", 14: "m:dQ,dP+"}
+cols = sorted(names)
 base = int(t[2, 0])
-print("tile " + " ".join("%14s" % n for n in names))
+print("pipelined kernel (attn_bwd2_kernel); SIDLSG_ATTN_BWD2=0 traces the first kernel with different slot meanings")
+print("tile " + " ".join("%10s" % names[c] for c in cols))
 for i in range(2, 14):
-    print("%4d " % i + " ".join("%14d" % (int(t[i, j]) - base) for j in range(len(names))))
+    print("%4d " % i + " ".join("%10d" % (int(t[i, c]) - base) for c in cols))
 print("period (c:s_full) per tile:", [int(t[i + 1, 1]) - int(t[i, 1]) for i in range(2, 13)])
+print("compute: wait S, exps+P, wait dP, dS:", [(int(t[i, 1]) - int(t[i, 0]), int(t[i, 2]) - int(t[i, 1]), int(t[i, 3]) - int(t[i, 2]), int(t[i, 4]) - int(t[i, 3])) for i in range(2, 8)])

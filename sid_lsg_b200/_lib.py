@@ -204,6 +204,13 @@ def stream():
 
 
 def require_cuda(*tensors):
+    """CUDA tensors on the CURRENT device only: the library launches on the current device's stream and keeps its
+    per-process kernel attributes for one device per process (one process per GPU, as torchrun runs it)."""
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("sid_lsg_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+        if t.device.index != torch.cuda.current_device():
+            raise RuntimeError("sid_lsg_b200 ops launch on the current CUDA device (%d); got a tensor on %s - call "
+                               "torch.cuda.set_device first" % (torch.cuda.current_device(), t.device))

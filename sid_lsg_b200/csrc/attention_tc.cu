@@ -67,6 +67,35 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// exp2 of two values on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5 - far
+// below the bf16 rounding P receives): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// 2^f ~ ((c3 f + c2) f + c1) f + c0 on [-0.5, 0.5], and n added into the exponent field.  The MUFU pipe (16 ex2 / clk / SM)
+// is what bounds the softmax loops (scripts/trace_attn_fwd.py: exponentials 2170 of 3300 clk per tile pair); moving a
+// fraction of the exponentials here lets both pipes work at once (FlashAttention-4's software exp2).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -125.f);                       // keeps the exponent arithmetic in range; 2^-125 is zero in bf16 anyway
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t t2 = fadd2(xc, pack2(12582912.f, 12582912.f));
+  const uint64_t n2 = fadd2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = ffma2(n2, pack2(-1.f, -1.f), xc);
+  uint64_t q2 = ffma2(f2, pack2(0.05517167f, 0.05517167f), pack2(0.24261113f, 0.24261113f));
+  q2 = ffma2(q2, f2, pack2(0.69326097f, 0.69326097f));
+  q2 = ffma2(q2, f2, pack2(0.99992806f, 0.99992806f));
+  float q0, q1, t0, t1;
+  unpack2(q2, q0, q1);
+  unpack2(t2, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+// which of the 16 score pairs of a 32-column chunk take the polynomial: NPOLY of 16, spread evenly
+template <int NPOLY>
+__device__ __forceinline__ constexpr bool poly_pair(int i2) {
+  return ((i2 + 1) * NPOLY) / 16 != (i2 * NPOLY) / 16;
+}
+
 template <int TCOLS>
 __global__ void __launch_bounds__(AT_THREADS, TCOLS == 256 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -362,7 +391,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 constexpr int A3_THREADS = 320;
 constexpr int A3_KST = 4, A3_VST = 4;
 
-template <bool TRACE>
+template <bool TRACE, int NPOLY>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -501,9 +530,16 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int i = 0; i < 32; i += 2) {
             const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
             mx = fmaxf(fmaxf(mx, x0), x1);
-            float t0, t1;
-            unpack2(ffma2(pack2(x0, x1), c2, nmc2), t0, t1);
-            const float p0 = ex2f(t0), p1 = ex2f(t1);
+            const uint64_t t2 = ffma2(pack2(x0, x1), c2, nmc2);
+            float p0, p1;
+            if (poly_pair<NPOLY>(i >> 1)) {
+              exp2_poly2(t2, p0, p1);
+            } else {
+              float t0, t1;
+              unpack2(t2, t0, t1);
+              p0 = ex2f(t0);
+              p1 = ex2f(t1);
+            }
             ls2 = fadd2(ls2, pack2(p0, p1));
             pk[i >> 1] = pack_bf16(p0, p1);
           }
@@ -671,14 +707,23 @@ static int attention_fwd_impl(const void* q, const void* k, const void* v, void*
   if (fwd3 && p.dpad <= 64) {
     static bool attr3 = false;
     if (!attr3) {
-      cudaFuncSetAttribute(attn_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(attn_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_fwd3_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr3 = true;
     }
     const int smem3 = (2 + A3_KST + A3_VST) * AT_CHUNK + 256;
     dim3 grid3((N + 2 * AT_BQ - 1) / (2 * AT_BQ), H, B);
-    if (trace) attn_fwd3_kernel<true><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
-    else attn_fwd3_kernel<false><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    // SIDLSG_ATTN_POLY = how many of every 16 exponentials run as a polynomial on the FMA pipe (0, 4, 6, 8; default 6)
+    static int npoly = -1;
+    if (npoly < 0) { const char* e = getenv("SIDLSG_ATTN_POLY"); npoly = e ? atoi(e) : 6; }
+    if (trace) attn_fwd3_kernel<true, 6><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    else if (npoly <= 0) attn_fwd3_kernel<false, 0><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    else if (npoly <= 4) attn_fwd3_kernel<false, 4><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    else if (npoly <= 6) attn_fwd3_kernel<false, 6><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
+    else attn_fwd3_kernel<false, 8><<<grid3, A3_THREADS, smem3, st>>>(tq, tk, tv, p);
     return check_launch("attention_fwd");
   }
   const int smem = (p.dchunks * (1 + 2 * p.kv_stages) + 2) * AT_CHUNK + 256;
@@ -1052,13 +1097,314 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward for d <= 64, pipelined (the phase trace of attn_bwd_kernel - scripts/trace_attn_bwd.py, profiles/ - showed its
+// 8 compute warps busy or waiting on each other for 4000 of the 4600 clk of a tile: exponentials 1530, dQ drain 1150
+// (two 256-thread barriers of skew), P^T store 480, dS 850, strictly in series with the 24 MMAs that follow).  Same
+// arithmetic and orientation, different choreography:
+//   * P^T is written IN PLACE over S^T in TMEM (bf16 pairs, tcgen05.st) and is the TMEM A operand of dV - no shared
+//     memory store, no wait for a free P tile;  dV(i) is issued as soon as P^T(i) exists, S^T(i+1) right behind it, so
+//     the next tile's scores are ready while the compute warps are still on dS(i);
+//   * dS^T is double buffered in shared memory, dQ double buffered in TMEM;
+//   * four dedicated drain warps move dQ(i) TMEM -> shared -> TMA reduce-add; the compute warps never touch it;
+//   * per-query statistics (-lse log2 e, -delta) arrive with the Q / dO tiles as TMA bulk copies: no per-tile 256-thread
+//     barrier is left in the compute loop.
+// 448 threads: warps 0-7 compute (two warpgroups split the 128 query columns), 8-11 dQ drain, 12 TMA, 13 MMA + TMEM.
+// TMEM: S^T/P^T 128 | dP^T 128 | dV | dK | dQ0 | dQ1 (dpad each) <= 512 columns.  Needs N % 128 == 0.
+constexpr int AB2_THREADS = 448;
+
+template <bool TRACE>
+__global__ void __launch_bounds__(AB2_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p, const float* __restrict__ nlse2) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t k_smem = smem_base;                       // 16 KB
+  const uint32_t v_smem = k_smem + AT_CHUNK;               // 16 KB
+  const uint32_t q_smem = v_smem + AT_CHUNK;               // 2 x 16 KB
+  const uint32_t do_smem = q_smem + 2 * AT_CHUNK;          // 2 x 16 KB
+  const uint32_t ds_smem = do_smem + 2 * AT_CHUNK;         // dS^T: 2 buffers x [128 kv][128 q] bf16 (2 chunks each)
+  const uint32_t dq_stage = ds_smem + 4 * AT_CHUNK;        // fp32 [chunks of 32 columns][128 rows][128 B], 2 chunks
+  const uint32_t stat_smem = dq_stage + 2 * AT_CHUNK;      // float [2 stages][nlse2 128 | ndelta 128]
+  const uint32_t bar_base = stat_smem + 2 * 1024;
+  const uint32_t kv_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, dp_full = bar_base + 24,
+                 ds_full = bar_base + 32, done_bar = bar_base + 40;
+  auto qdo_full = [&](int s) { return bar_base + 48 + 8u * s; };
+  auto qdo_empty = [&](int s) { return bar_base + 64 + 8u * s; };
+  auto dq_full = [&](int s) { return bar_base + 80 + 8u * s; };
+  auto dq_empty = [&](int s) { return bar_base + 96 + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 112;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  const float* stat = reinterpret_cast<const float*>(smem_raw + (stat_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * AT_BKV, h = blockIdx.y, b = blockIdx.z;
+  const int TQ = p.N / AT_BQ;
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) { printf("sidlsg attention bwd: dynamic smem not 1024-aligned\n"); __trap(); }
+    mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(dp_full, 1); mbar_init(ds_full, 8);
+    mbar_init(done_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); mbar_init(dq_full(s), 1); mbar_init(dq_empty(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 13) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t st_tmem = tmem_base, dp_tmem = tmem_base + 128, dv_tmem = tmem_base + 256,
+                 dk_tmem = tmem_base + 256 + p.dpad;
+  auto dq_tmem = [&](int s) { return tmem_base + 256 + (2 + s) * p.dpad; };
+
+  if (warp == 12) {
+    // ===================== TMA producer =====================
+    if (role_leader()) {
+      mbar_expect_tx(kv_full, 2 * AT_CHUNK);
+      tma_load_4d(&tmK, kv_full, k_smem, 0, h, kv0, b);
+      tma_load_4d(&tmV, kv_full, v_smem, 0, h, kv0, b);
+      const long srow = ((long)b * p.H + h) * p.N;
+      for (int i = 0; i < TQ; ++i) {
+        const int st = i & 1;
+        mbar_wait_h(p.wait_hint, qdo_empty(st), ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full(st), 2 * AT_CHUNK + 1024);
+        tma_load_4d(&tmQ, qdo_full(st), q_smem + st * AT_CHUNK, 0, h, i * AT_BQ, b);
+        tma_load_4d(&tmDO, qdo_full(st), do_smem + st * AT_CHUNK, 0, h, i * AT_BQ, b);
+        bulk_load_1d(stat_smem + st * 1024, nlse2 + srow + (long)i * AT_BQ, 512, qdo_full(st));
+        bulk_load_1d(stat_smem + st * 1024 + 512, p.delta + srow + (long)i * AT_BQ, 512, qdo_full(st));
+      }
+    }
+  } else if (warp == 13) {
+    // ===================== MMA issuer =====================
+    if (role_leader()) {
+      const int dsteps = p.dpad >> 4;
+      const uint32_t idesc_s = make_idesc(128, 0, 0);
+      const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
+      const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
+      auto issue_s = [&](int i) {          // S^T_i = K Q_i^T
+        const uint32_t qb = q_smem + (i & 1) * AT_CHUNK;
+        for (int s = 0; s < dsteps; ++s)
+          tc_mma_bf16(st_tmem, make_desc(k_smem + s * 32, 1024, 0), make_desc(qb + s * 32, 1024, 0), idesc_s, s > 0);
+        tc_commit(s_full);
+      };
+      auto issue_dp = [&](int i) {         // dP^T_i = V dO_i^T
+        const uint32_t dob = do_smem + (i & 1) * AT_CHUNK;
+        for (int s = 0; s < dsteps; ++s)
+          tc_mma_bf16(dp_tmem, make_desc(v_smem + s * 32, 1024, 0), make_desc(dob + s * 32, 1024, 0), idesc_s, s > 0);
+        tc_commit(dp_full);
+      };
+      mbar_wait_h(p.wait_hint, kv_full, 0);
+      mbar_wait_h(p.wait_hint, qdo_full(0), 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < TQ; ++i) {
+        const int st = i & 1;
+        const uint32_t qb = q_smem + st * AT_CHUNK, dob = do_smem + st * AT_CHUNK, dsb = ds_smem + st * 2 * AT_CHUNK;
+        const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
+        if (tr) p.trace[i * 16 + 8] = clock64();
+        mbar_wait_h(p.wait_hint, p_full, i & 1);
+        if (tr) p.trace[i * 16 + 9] = clock64();
+        tc_fence_after();
+        for (int s = 0; s < 8; ++s)        // dV += P^T_i dO_i: A = P^T from TMEM (queries 0-63 at columns 0.., 64-127 at 64..)
+          tc_mma_bf16_ta(dv_tmem, st_tmem + (s >> 2) * 64 + (s & 3) * 8, make_desc(dob + s * 2048, 1024, AT_CHUNK),
+                         idesc_kv, (i > 0 || s > 0) ? 1u : 0u);
+        if (i + 1 < TQ) {                  // the next tile's scores overwrite P^T_i right behind the product that read it
+          mbar_wait_h(p.wait_hint, qdo_full((i + 1) & 1), ((i + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
+        if (tr) p.trace[i * 16 + 10] = clock64();
+        mbar_wait_h(p.wait_hint, ds_full, i & 1);
+        if (tr) p.trace[i * 16 + 11] = clock64();
+        tc_fence_after();
+        for (int s = 0; s < 8; ++s) {      // dK += dS^T_i Q_i
+          const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
+          tc_mma_bf16(dk_tmem, make_desc(dsb + aoff, 1024, 0), make_desc(qb + s * 2048, 1024, AT_CHUNK), idesc_kv,
+                      (i > 0 || s > 0) ? 1u : 0u);
+        }
+        if (tr) p.trace[i * 16 + 12] = clock64();
+        mbar_wait_h(p.wait_hint, dq_empty(st), ((i >> 1) & 1) ^ 1);   // the drain warps have read dQ_{i-2}
+        if (tr) p.trace[i * 16 + 13] = clock64();
+        tc_fence_after();
+        for (int s = 0; s < 8; ++s)        // dQ_i = dS_i K (reduction over the 128 kv rows)
+          tc_mma_bf16(dq_tmem(st), make_desc(dsb + s * 2048, 1024, AT_CHUNK), make_desc(k_smem + s * 2048, 1024, AT_CHUNK),
+                      idesc_dq, s > 0);
+        tc_commit(qdo_empty(st));
+        tc_commit(dq_full(st));
+        if (i + 1 < TQ) issue_dp(i + 1);
+        if (tr) p.trace[i * 16 + 14] = clock64();
+      }
+      tc_commit(done_bar);
+    }
+  } else if (warp >= 8) {
+    // ===================== dQ drain (warps 8-11: TMEM lane quarter = warp & 3 = 32 query rows) =====================
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const int rx = row & 7;
+    const int dq_chunks = (p.d + 31) >> 5;
+    const bool leader = threadIdx.x == 256;
+    for (int i = 0; i < TQ; ++i) {
+      const int st = i & 1;
+      mbar_wait(dq_full(st), (i >> 1) & 1);
+      if (TRACE && leader && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32) p.trace[i * 16 + 6] = clock64();
+      tc_fence_after();
+      if (leader) tma_wait_group_read0();          // the previous reduce has finished reading the staging tile
+      named_bar_sync(3, 128);
+      for (int blk = 0; blk * 16 < p.dpad; ++blk) {
+        uint32_t r[16];
+        tmem_ld16_nowait(dq_tmem(st) + lane_off + blk * 16, r);
+        tmem_wait_ld();
+        const uint32_t base = dq_stage + (blk >> 1) * AT_CHUNK + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(base + ((((blk & 1) * 4 + j) ^ rx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty(st));    // this dQ accumulator may be overwritten (tile i + 2)
+      named_bar_sync(3, 128);
+      if (leader) {
+        for (int ch = 0; ch < dq_chunks; ++ch) tma_reduce_add_4d(&tmDQ, dq_stage + ch * AT_CHUNK, ch * 32, h, i * AT_BQ, b);
+        tma_commit_group();
+        if (TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32) p.trace[i * 16 + 7] = clock64();
+      }
+    }
+    if (leader) tma_wait_group0();
+  } else {
+    // ===================== compute warps 0-7 =====================
+    const int wg = warp >> 2;                       // which 64 query columns
+    const int row = (warp & 3) * 32 + lane;         // kv row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bool row_ok = kv0 + row < p.M;
+    const uint64_t c2 = pack2(p.scale_log2, p.scale_log2), scale2 = pack2(p.scale, p.scale);
+    const int rx = row & 7;
+    for (int i = 0; i < TQ; ++i) {
+      const int st = i & 1;
+      const float* nlse = stat + st * 256 + wg * 64;
+      const float* ndl = stat + st * 256 + 128 + wg * 64;
+      const uint32_t ds_row = ds_smem + st * 2 * AT_CHUNK + wg * AT_CHUNK + row * 128;
+      uint64_t ps2[32];                      // P * scale for this thread's 64 query columns (fp32 pairs)
+      const bool tr = TRACE && threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
+      if (tr) p.trace[i * 16 + 0] = clock64();
+      mbar_wait(qdo_full(st), (i >> 1) & 1); // the statistics of this query tile have landed
+      mbar_wait(s_full, i & 1);
+      if (tr) p.trace[i * 16 + 1] = clock64();
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32], pk[16];
+        tmem_ld32_nowait(st_tmem + lane_off + wg * 64 + half * 32, r);
+        float4 nlv[8];                        // statistics fetched while the TMEM load is in flight
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nlv[j] = *reinterpret_cast<const float4*>(nlse + half * 32 + 4 * j);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 nl = nlv[j >> 2];
+          float t0, t1, t2, t3;
+          unpack2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(nl.x, nl.y)), t0, t1);
+          unpack2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), t2, t3);
+          float p0 = ex2f(t0), p1 = ex2f(t1), p2 = ex2f(t2), p3 = ex2f(t3);
+          if (!row_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+          pk[j >> 1] = pack_bf16(p0, p1);
+          pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+          ps2[half * 16 + (j >> 1)] = fmul2(pack2(p0, p1), scale2);
+          ps2[half * 16 + (j >> 1) + 1] = fmul2(pack2(p2, p3), scale2);
+        }
+        // P^T in place (bf16 pairs): half h lands on columns [wg*64 + 16h, +16) - all inside [wg*64, wg*64 + 32), which
+        // this thread finished reading with its first load, and nobody else touches this lane's columns of this warpgroup
+        tmem_st16(st_tmem + lane_off + wg * 64 + half * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (tr) p.trace[i * 16 + 2] = clock64();
+      mbar_wait(dp_full, i & 1);
+      if (tr) p.trace[i * 16 + 3] = clock64();
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32], dsk[16];
+        tmem_ld32_nowait(dp_tmem + lane_off + wg * 64 + half * 32, r);
+        float4 ndv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ndv[j] = *reinterpret_cast<const float4*>(ndl + half * 32 + 4 * j);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 nd = ndv[j >> 2];
+          float d0, d1, d2, d3;
+          unpack2(fmul2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(nd.x, nd.y)),
+                        ps2[half * 16 + (j >> 1)]), d0, d1);
+          unpack2(fmul2(fadd2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pack2(nd.z, nd.w)),
+                        ps2[half * 16 + (j >> 1) + 1]), d2, d3);
+          dsk[j >> 1] = pack_bf16(d0, d1);
+          dsk[(j >> 1) + 1] = pack_bf16(d2, d3);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          st_shared_v4(ds_row + (((half * 4 + qd) ^ rx) << 4), dsk[4 * qd], dsk[4 * qd + 1], dsk[4 * qd + 2],
+                       dsk[4 * qd + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      if (tr) p.trace[i * 16 + 4] = clock64();
+    }
+    // every MMA has retired: dV / dK accumulators are final.  wg0 stores dV, wg1 stores dK.
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    {
+      const uint32_t acc = wg == 0 ? dv_tmem : dk_tmem;
+      bf16* out = (wg == 0 ? p.dv : p.dk) + ((long)b * p.M + kv0 + row) * (wg == 0 ? p.lddv : p.lddk) + h * p.d;
+      for (int cc = 0; cc < p.dpad; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(acc + lane_off + cc, r);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (cc + 8 * hh < p.d) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(r[8 * hh + 0]), __uint_as_float(r[8 * hh + 1]));
+              o.y = pack_bf16(__uint_as_float(r[8 * hh + 2]), __uint_as_float(r[8 * hh + 3]));
+              o.z = pack_bf16(__uint_as_float(r[8 * hh + 4]), __uint_as_float(r[8 * hh + 5]));
+              o.w = pack_bf16(__uint_as_float(r[8 * hh + 6]), __uint_as_float(r[8 * hh + 7]));
+              *reinterpret_cast<uint4*>(out + cc + 8 * hh) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // delta[b,h,q] = sum_c O[b,q,h*d+c] * dO[b,q,h*d+c].  A block takes `rows` consecutive (b,q) rows; thread = one
 // 16-byte piece (8 channels, never straddling a head since d % 8 == 0) of one row, so the block reads contiguous
 // memory; the d/8 piece sums of a head meet in shared memory.  (The one-warp-per-(b,q,h) version moved 80-byte
 // segments per warp and ran at 0.9 TB/s.)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, long BN, int N,
-                  int H, int d, int ppr, int rows) {
+                  int H, int d, int ppr, int rows, const float* __restrict__ lse, float* __restrict__ nlse2) {
   __shared__ float part[256];
   const int t = threadIdx.x;
   const int rl = t / ppr, piece = t - rl * ppr;
@@ -1085,7 +1431,11 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, flo
       float acc = 0.f;
       for (int i = 0; i < pph; ++i) acc += pp[i];
       const long bb = row2 / N, q = row2 - bb * N;
-      delta[(bb * H + hh) * N + q] = acc;
+      const long gi = (bb * H + hh) * N + q;
+      // nlse2 given (two-stage-pipelined backward): statistics are stored NEGATED, lse in the log2 domain, so they feed
+      // the packed FFMA2 / FADD2 of the consumer directly and travel as plain TMA bulk copies
+      delta[gi] = nlse2 ? -acc : acc;
+      if (nlse2) nlse2[gi] = lse[gi] * -1.4426950408889634f;
     }
   }
 }
@@ -1108,7 +1458,7 @@ static bool g_attn_bwd_attr_done = false;
 
 }  // namespace sidlsg
 
-// dq_acc: fp32 [B,N,H*d] scratch (zeroed here), delta: fp32 [B,H,N] scratch.  dq/dk/dv bf16 outputs.
+// dq_acc: fp32 [B,N,H*d] scratch (zeroed here), delta: fp32 [2,B,H,N] scratch (delta and -lse log2 e).  dq/dk/dv bf16.
 // q/k/v and dq/dk/dv may be column slices of packed tensors: ld* = their row strides in elements (o, dout dense).
 // Supports d % 8 == 0, 16 <= d <= 80 (TMEM: 256 + 3*dpad <= 512 columns); returns SIDLSG_ERR_UNSUPPORTED otherwise.
 static int attention_bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* dout,
@@ -1131,13 +1481,18 @@ static int attention_bwd_impl(const void* q, const void* k, const void* v, const
   }
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * N * H * d, st);
+  // d <= 64 and whole query tiles: the pipelined kernel (attn_bwd2_kernel); SIDLSG_ATTN_BWD2=0 keeps the first one (A/B)
+  static int bwd2 = -1;
+  if (bwd2 < 0) { const char* e = getenv("SIDLSG_ATTN_BWD2"); bwd2 = (e && e[0] == '0') ? 0 : 1; }
+  const bool use_bwd2 = bwd2 && dpad <= 64 && (N % AT_BQ) == 0;
+  float* nlse2 = delta + (size_t)B * H * N;          // second half of the statistics scratch
   {
     const int ppr = H * d / 8;                       // 16-byte pieces per (b,q) row; H*d <= 2048 on this path
     if (ppr > 256) { set_error("attention_bwd: H*d = %d too wide for the delta kernel", H * d); return SIDLSG_ERR_UNSUPPORTED; }
     const int rows = 256 / ppr;
     const long BN = (long)B * N;
     attn_delta_kernel<<<(unsigned)((BN + rows - 1) / rows), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, BN, N,
-                                                                             H, d, ppr, rows);
+                                                                             H, d, ppr, rows, lse, use_bwd2 ? nlse2 : nullptr);
   }
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
@@ -1171,7 +1526,17 @@ static int attention_bwd_impl(const void* q, const void* k, const void* v, const
     g_attn_bwd_attr_done = true;
   }
   dim3 grid((M + AT_BKV - 1) / AT_BKV, H, B);
-  if (trace) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  if (use_bwd2) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(attn_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(attn_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr2 = true;
+    }
+    const int smem2 = 12 * AT_CHUNK + 2 * 1024 + 256;
+    if (trace) attn_bwd2_kernel<true><<<grid, AB2_THREADS, smem2, st>>>(tq, tk, tv, tdo, tdq, p, nlse2);
+    else attn_bwd2_kernel<false><<<grid, AB2_THREADS, smem2, st>>>(tq, tk, tv, tdo, tdq, p, nlse2);
+  } else if (trace) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   else attn_bwd_kernel<false><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   int r = check_launch("attention_bwd");
   if (r != SIDLSG_OK) return r;

@@ -396,7 +396,7 @@ def _attention_backward(q, k, v, extra, flash_bwd, do, heads, dq, dk, dv, split=
     do = _c(do)
     if flash_bwd:
         o, lse = extra
-        delta = torch.empty_like(lse)
+        delta = torch.empty((2,) + tuple(lse.shape), dtype=lse.dtype, device=lse.device)   # delta | -lse log2(e)
         dq_acc = torch.empty((B, N, C), dtype=torch.float32, device=q.device)
         lib.call("attention_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dq_acc),
                  ptr(dq), ptr(dk), ptr(dv), B, N, M, heads, d, _rows(q), _rows(k), _rows(v), _rows(dq), _rows(dk),

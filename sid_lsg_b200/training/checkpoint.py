@@ -14,8 +14,11 @@ What the reference reads and writes, and what this module does about it:
 * **`training-state-*.pt`** - `torch.save(dict(fake_score=, G=, G_ema=, fake_score_optimizer_state=,
   g_optimizer_state=))` (:654-656), restored at :296-310.  `save_training_state` / `load_training_state` keep the same
   five keys; the networks are state dicts and the two optimiser entries are in `torch.optim.Adam.state_dict()`
-  layout (`adam_state_dict`: per-parameter `step`, `exp_avg`, `exp_avg_sq` + one param group), so the reference's
-  `fake_score_optimizer.load_state_dict(...)` accepts them and its own dumps load here (`load_adam_state_dict`).
+  layout (`adam_state_dict`: per-parameter `step`, `exp_avg`, `exp_avg_sq` + one param group, indexed in
+  `parameters()` order - which unet.py keeps equal to diffusers 0.27.2's registration order, see
+  tests/test_surface_cpu.py::test_parameter_order_is_diffusers_order), so the reference's
+  `fake_score_optimizer.load_state_dict(...)` accepts them and its own dumps load here (`load_adam_state_dict`, which
+  checks every state tensor's shape against its parameter).
 
 Everything is host-side I/O; tensors are moved with plain copies (the flat buckets are the only device state).
 """
@@ -211,6 +214,10 @@ def load_adam_state_dict(sd, params, exp_avg_sq, offsets, exp_avg=None):
             if bucket is None:
                 continue
             view = torch.as_strided(bucket, p.shape, p.stride(), off)
+            if tuple(st[src_key].shape) != tuple(p.shape):
+                raise ValueError("optimizer state %d (%s): shape %s does not match parameter shape %s - the state dict "
+                                 "was written for a different parameter order" % (i, src_key, tuple(st[src_key].shape),
+                                                                               tuple(p.shape)))
             view.copy_(st[src_key].to(view.device, torch.float32))
     return step
 
