@@ -1,0 +1,6 @@
+#!/bin/bash
+OUT=gpurun_out/r2g; mkdir -p $OUT
+timeout 120 python scripts/trace_attn_bwd.py > $OUT/trace_bwd2.txt 2>&1; cat $OUT/trace_bwd2.txt
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_unet_step_gpu.py -m gpu -q -x -p no:cacheprovider > $OUT/pytest.log 2>&1; tail -8 $OUT/pytest.log
+for f in 0 1; do echo "== SIDLSG_GN_FUSED=$f"; SIDLSG_GN_FUSED=$f timeout 300 python scripts/micro.py gn 10 2>&1 | tee $OUT/micro_gn_$f.txt; done
+timeout 900 python bench.py --no-cpu-baseline --steps 3 --shapes $OUT/shapes.txt > $OUT/bench.json 2> $OUT/bench.err; tail -c 400 $OUT/bench.err; python scripts/bench_brief.py $OUT/bench.json

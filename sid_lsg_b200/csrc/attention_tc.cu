@@ -1112,6 +1112,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // 448 threads: warps 0-7 compute (two warpgroups split the 128 query columns), 8-11 dQ drain, 12 TMA, 13 MMA + TMEM.
 // TMEM: S^T/P^T 128 | dP^T 128 | dV | dK | dQ0 | dQ1 (dpad each) <= 512 columns.  Needs N % 128 == 0.
 constexpr int AB2_THREADS = 448;
+constexpr int AB2_QST = 3;
 
 template <bool TRACE>
 __global__ void __launch_bounds__(AB2_THREADS, 1)
@@ -1122,19 +1123,23 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t k_smem = smem_base;                       // 16 KB
   const uint32_t v_smem = k_smem + AT_CHUNK;               // 16 KB
-  const uint32_t q_smem = v_smem + AT_CHUNK;               // 2 x 16 KB
-  const uint32_t do_smem = q_smem + 2 * AT_CHUNK;          // 2 x 16 KB
+  const uint32_t q_smem = v_smem + AT_CHUNK;               // AB2_QST x 16 KB (Q is held from S^T_i to dK_i: 3 stages)
+  const uint32_t do_smem = q_smem + AB2_QST * AT_CHUNK;    // 2 x 16 KB (dO is released after dV_i, half a tile earlier)
   const uint32_t ds_smem = do_smem + 2 * AT_CHUNK;         // dS^T: 2 buffers x [128 kv][128 q] bf16 (2 chunks each)
   const uint32_t dq_stage = ds_smem + 4 * AT_CHUNK;        // fp32 [chunks of 32 columns][128 rows][128 B], 2 chunks
-  const uint32_t stat_smem = dq_stage + 2 * AT_CHUNK;      // float [2 stages][nlse2 128 | ndelta 128]
-  const uint32_t bar_base = stat_smem + 2 * 1024;
+  const uint32_t stat_smem = dq_stage + 2 * AT_CHUNK;      // float [2 stages][nlse2 128 | ndelta 128], own ring (released by
+  const uint32_t bar_base = stat_smem + 2 * 1024;          // the compute warps after dS_i; 227 KB leaves no room for a third)
   const uint32_t kv_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, dp_full = bar_base + 24,
                  ds_full = bar_base + 32, done_bar = bar_base + 40;
-  auto qdo_full = [&](int s) { return bar_base + 48 + 8u * s; };
-  auto qdo_empty = [&](int s) { return bar_base + 64 + 8u * s; };
-  auto dq_full = [&](int s) { return bar_base + 80 + 8u * s; };
-  auto dq_empty = [&](int s) { return bar_base + 96 + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 112;
+  auto q_full = [&](int s) { return bar_base + 48 + 8u * s; };       // [AB2_QST]
+  auto q_empty = [&](int s) { return bar_base + 80 + 8u * s; };
+  auto do_full = [&](int s) { return bar_base + 112 + 8u * s; };     // [2]
+  auto do_empty = [&](int s) { return bar_base + 128 + 8u * s; };
+  auto dq_full = [&](int s) { return bar_base + 144 + 8u * s; };
+  auto dq_empty = [&](int s) { return bar_base + 160 + 8u * s; };
+  auto stat_full = [&](int s) { return bar_base + 176 + 8u * s; };
+  auto stat_empty = [&](int s) { return bar_base + 192 + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 208;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
   const float* stat = reinterpret_cast<const float*>(smem_raw + (stat_smem - smem_base));
 
@@ -1146,8 +1151,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (smem_base & 1023u) { printf("sidlsg attention bwd: dynamic smem not 1024-aligned\n"); __trap(); }
     mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(dp_full, 1); mbar_init(ds_full, 8);
     mbar_init(done_bar, 1);
+    for (int s = 0; s < AB2_QST; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); mbar_init(dq_full(s), 1); mbar_init(dq_empty(s), 4);
+      mbar_init(do_full(s), 1); mbar_init(do_empty(s), 1); mbar_init(dq_full(s), 1); mbar_init(dq_empty(s), 4);
+      mbar_init(stat_full(s), 1); mbar_init(stat_empty(s), 8);
     }
     fence_barrier_init();
   }
@@ -1172,13 +1179,17 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_load_4d(&tmV, kv_full, v_smem, 0, h, kv0, b);
       const long srow = ((long)b * p.H + h) * p.N;
       for (int i = 0; i < TQ; ++i) {
-        const int st = i & 1;
-        mbar_wait_h(p.wait_hint, qdo_empty(st), ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(qdo_full(st), 2 * AT_CHUNK + 1024);
-        tma_load_4d(&tmQ, qdo_full(st), q_smem + st * AT_CHUNK, 0, h, i * AT_BQ, b);
-        tma_load_4d(&tmDO, qdo_full(st), do_smem + st * AT_CHUNK, 0, h, i * AT_BQ, b);
-        bulk_load_1d(stat_smem + st * 1024, nlse2 + srow + (long)i * AT_BQ, 512, qdo_full(st));
-        bulk_load_1d(stat_smem + st * 1024 + 512, p.delta + srow + (long)i * AT_BQ, 512, qdo_full(st));
+        const int qs = i % AB2_QST, ds = i & 1;
+        mbar_wait_h(p.wait_hint, q_empty(qs), ((i / AB2_QST) & 1) ^ 1);
+        mbar_expect_tx(q_full(qs), AT_CHUNK);
+        tma_load_4d(&tmQ, q_full(qs), q_smem + qs * AT_CHUNK, 0, h, i * AT_BQ, b);
+        mbar_wait_h(p.wait_hint, stat_empty(ds), ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(stat_full(ds), 1024);
+        bulk_load_1d(stat_smem + ds * 1024, nlse2 + srow + (long)i * AT_BQ, 512, stat_full(ds));
+        bulk_load_1d(stat_smem + ds * 1024 + 512, p.delta + srow + (long)i * AT_BQ, 512, stat_full(ds));
+        mbar_wait_h(p.wait_hint, do_empty(ds), ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(do_full(ds), AT_CHUNK);
+        tma_load_4d(&tmDO, do_full(ds), do_smem + ds * AT_CHUNK, 0, h, i * AT_BQ, b);
       }
     }
   } else if (warp == 13) {
@@ -1189,7 +1200,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
       const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
       auto issue_s = [&](int i) {          // S^T_i = K Q_i^T
-        const uint32_t qb = q_smem + (i & 1) * AT_CHUNK;
+        const uint32_t qb = q_smem + (i % AB2_QST) * AT_CHUNK;
         for (int s = 0; s < dsteps; ++s)
           tc_mma_bf16(st_tmem, make_desc(k_smem + s * 32, 1024, 0), make_desc(qb + s * 32, 1024, 0), idesc_s, s > 0);
         tc_commit(s_full);
@@ -1201,13 +1212,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_commit(dp_full);
       };
       mbar_wait_h(p.wait_hint, kv_full, 0);
-      mbar_wait_h(p.wait_hint, qdo_full(0), 0);
+      mbar_wait_h(p.wait_hint, q_full(0), 0);
       tc_fence_after();
       issue_s(0);
+      mbar_wait_h(p.wait_hint, do_full(0), 0);
+      tc_fence_after();
       issue_dp(0);
       for (int i = 0; i < TQ; ++i) {
-        const int st = i & 1;
-        const uint32_t qb = q_smem + st * AT_CHUNK, dob = do_smem + st * AT_CHUNK, dsb = ds_smem + st * 2 * AT_CHUNK;
+        const int st = i & 1, qs = i % AB2_QST;
+        const uint32_t qb = q_smem + qs * AT_CHUNK, dob = do_smem + st * AT_CHUNK, dsb = ds_smem + st * 2 * AT_CHUNK;
         const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
         if (tr) p.trace[i * 16 + 8] = clock64();
         mbar_wait_h(p.wait_hint, p_full, i & 1);
@@ -1216,8 +1229,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int s = 0; s < 8; ++s)        // dV += P^T_i dO_i: A = P^T from TMEM (queries 0-63 at columns 0.., 64-127 at 64..)
           tc_mma_bf16_ta(dv_tmem, st_tmem + (s >> 2) * 64 + (s & 3) * 8, make_desc(dob + s * 2048, 1024, AT_CHUNK),
                          idesc_kv, (i > 0 || s > 0) ? 1u : 0u);
+        tc_commit(do_empty(st));           // dO_i has been read for the last time once dV_i retires
         if (i + 1 < TQ) {                  // the next tile's scores overwrite P^T_i right behind the product that read it
-          mbar_wait_h(p.wait_hint, qdo_full((i + 1) & 1), ((i + 1) >> 1) & 1);
+          mbar_wait_h(p.wait_hint, q_full((i + 1) % AB2_QST), ((i + 1) / AB2_QST) & 1);
           tc_fence_after();
           issue_s(i + 1);
         }
@@ -1237,9 +1251,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int s = 0; s < 8; ++s)        // dQ_i = dS_i K (reduction over the 128 kv rows)
           tc_mma_bf16(dq_tmem(st), make_desc(dsb + s * 2048, 1024, AT_CHUNK), make_desc(k_smem + s * 2048, 1024, AT_CHUNK),
                       idesc_dq, s > 0);
-        tc_commit(qdo_empty(st));
+        tc_commit(q_empty(qs));
         tc_commit(dq_full(st));
-        if (i + 1 < TQ) issue_dp(i + 1);
+        if (i + 1 < TQ) {
+          mbar_wait_h(p.wait_hint, do_full((i + 1) & 1), ((i + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_dp(i + 1);
+        }
         if (tr) p.trace[i * 16 + 14] = clock64();
       }
       tc_commit(done_bar);
@@ -1296,7 +1314,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint64_t ps2[32];                      // P * scale for this thread's 64 query columns (fp32 pairs)
       const bool tr = TRACE && threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
       if (tr) p.trace[i * 16 + 0] = clock64();
-      mbar_wait(qdo_full(st), (i >> 1) & 1); // the statistics of this query tile have landed
+      mbar_wait(stat_full(st), (i >> 1) & 1);    // the statistics of this query tile have landed
       mbar_wait(s_full, i & 1);
       if (tr) p.trace[i * 16 + 1] = clock64();
       tc_fence_after();
@@ -1360,7 +1378,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) { mbar_arrive(ds_full); mbar_arrive(stat_empty(st)); }
       if (tr) p.trace[i * 16 + 4] = clock64();
     }
     // every MMA has retired: dV / dK accumulators are final.  wg0 stores dV, wg1 stores dK.
@@ -1533,7 +1551,7 @@ static int attention_bwd_impl(const void* q, const void* k, const void* v, const
       cudaFuncSetAttribute(attn_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr2 = true;
     }
-    const int smem2 = 12 * AT_CHUNK + 2 * 1024 + 256;
+    const int smem2 = (11 + AB2_QST) * AT_CHUNK + 2 * 1024 + 256;
     if (trace) attn_bwd2_kernel<true><<<grid, AB2_THREADS, smem2, st>>>(tq, tk, tv, tdo, tdq, p, nlse2);
     else attn_bwd2_kernel<false><<<grid, AB2_THREADS, smem2, st>>>(tq, tk, tv, tdo, tdq, p, nlse2);
   } else if (trace) attn_bwd_kernel<true><<<grid, AB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);

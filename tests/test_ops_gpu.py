@@ -319,3 +319,33 @@ def test_no_cpu_fallback():
     w = torch.nn.Parameter(torch.randn(8, 8))
     with pytest.raises(RuntimeError):
         ops().linear(x, w)
+
+
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("B,HW,C,G", [(2, 4096, 320, 32), (2, 1024, 640, 32), (1, 4096, 960, 32), (2, 256, 1280, 32),
+                                      (3, 64, 2560, 32), (2, 1024, 1920, 32), (2, 256, 32, 8), (5, 100, 64, 8)])
+def test_groupnorm_bf16_sd_shapes(B, HW, C, G, silu):
+    """bf16 GroupNorm (+SiLU) forward / backward at the SD shapes vs fp32 torch on the bf16-rounded input."""
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, HW, C, generator=g) * 2 + 0.5).bfloat16().float()
+    ga = torch.randn(C, generator=g)
+    be = torch.randn(C, generator=g)
+    dy = torch.randn(B, HW, C, generator=g).bfloat16().float()
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, ga, be))
+    yr = F.group_norm(xr.transpose(1, 2), G, gr, br, 1e-5)
+    if silu:
+        yr = F.silu(yr)
+    yr = yr.transpose(1, 2)
+    yr.backward(dy)
+    xd = x.to(DEV).bfloat16().requires_grad_(True)
+    gp, bp = P(ga), P(be)
+    y = ops().group_norm(xd, gp, bp, G, 1e-5, silu)
+    y.backward(dy.to(DEV).bfloat16())
+
+    def relerr(a, b):
+        a, b = a.detach().float().cpu(), b.detach().float().cpu()
+        return float((a - b).norm() / b.norm().clamp_min(1e-20))
+    assert relerr(y, yr) < 6e-3, relerr(y, yr)                  # bf16 output rounding
+    assert relerr(xd.grad, xr.grad) < 6e-3, relerr(xd.grad, xr.grad)
+    assert relerr(gp.grad, gr.grad) < 2e-3, relerr(gp.grad, gr.grad)   # fp32 accumulations of bf16 inputs
+    assert relerr(bp.grad, br.grad) < 2e-3, relerr(bp.grad, br.grad)
