@@ -482,11 +482,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait_h(p.wait_hint, p_full(x), j & 1);
           if (tr) p.trace[j * 16 + 9 + 3 * x] = clock64();
           tc_fence_after();
+          // S_X(j) has been consumed (P_X(j) exists): the NEXT tile's scores go first, so the softmax warps get them
+          // ~330 clk after their arrival instead of after the 8 + 3 MMAs of P V and Q K^T (their exponentials of tile
+          // j + 1 then run under P_X(j) V_j; they wait on o_full before touching P_X or O_X again)
+          if (more) issue_qk(x, j + 1);
           for (int s2 = 0; s2 < ksteps; ++s2)
             tc_mma_bf16_ta(o_tmem(x), p_tmem(x) + s2 * 8, make_desc(vb + s2 * 2048, 1024, AT_CHUNK), idesc_pv,
                            (j > 0 || s2 > 0) ? 1u : 0u);
           tc_commit(o_full(x));
-          if (more) issue_qk(x, j + 1);
           if (tr) p.trace[j * 16 + 10 + 3 * x] = clock64();
         }
         tc_commit(v_empty(vs));
@@ -515,17 +518,30 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       return mx;
     };
     // P = exp2(s*c - m*c) -> bf16 pairs in TMEM; returns the row sum, tracks the raw row max in mx
-    auto tile_exp = [&](int n_valid, float m, float& mx) {
+    bool pv_pending = false;     // P_X V_{j-1} may still be reading P_X / writing O_X
+    auto wait_pv = [&](int j) {
+      if (pv_pending) {
+        mbar_wait(o_full(x), (j - 1) & 1);
+        tc_fence_after();
+        pv_pending = false;
+      }
+    };
+    auto tile_exp = [&](int n_valid, float m, float& mx, int j) {
       const float nmc = -m * c;
       const uint64_t nmc2 = pack2(nmc, nmc);
       float ls = 0.f;
       if (n_valid == AT_BKV) {
         uint64_t ls2 = pack2(0.f, 0.f);
+        // software-pipelined over the four 32-column chunks: the TMEM load of chunk k + 1 is in flight while chunk k is
+        // exponentiated (two register buffers; a warp has only one partner warp on its scheduler to hide that latency)
+        uint32_t rbuf[2][32];
+        tmem_ld32_nowait(st, rbuf[0]);
 #pragma unroll
         for (int cc = 0; cc < AT_BKV; cc += 32) {
-          uint32_t r[32], pk[16];
-          tmem_ld32_nowait(st + cc, r);
-          tmem_wait_ld();
+          uint32_t* r = rbuf[(cc >> 5) & 1];
+          uint32_t pk[16];
+          tmem_wait_ld_dep32(r);
+          if (cc + 32 < AT_BKV) tmem_ld32_nowait(st + cc + 32, rbuf[((cc >> 5) + 1) & 1]);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
@@ -543,6 +559,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ls2 = fadd2(ls2, pack2(p0, p1));
             pk[i >> 1] = pack_bf16(p0, p1);
           }
+          wait_pv(j);
           tmem_st16(pt + (cc >> 1), pk);
         }
         float a0, a1;
@@ -564,6 +581,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ls += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
+          wait_pv(j);
           tmem_st16(pt + (cc >> 1), pk);
         }
       }
@@ -585,25 +603,27 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
       const bool spec = j > 0 && n_valid == AT_BKV;
-      // s_full(j) is committed AFTER P_X V_{j-1} was issued, so its arrival also means that product has retired:
-      // O_X and the P_X region are ours again (no separate o_full wait on the critical path)
+      // S_X(j) is issued BEFORE P_X V_{j-1}: that product may still be running when the scores arrive, so O_X and the
+      // P_X region are touched only after o_full (wait_pv below; by then most of the first 32 columns are done)
       const bool tr = TRACE && (threadIdx.x & 127) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
       if (tr) p.trace[j * 16 + 4 * x] = clock64();
       mbar_wait(s_full(x), j & 1);
       if (tr) p.trace[j * 16 + 4 * x + 1] = clock64();
       tc_fence_after();
+      pv_pending = j > 0;
       if (!spec) {
         const float m_new = fmaxf(m_used, tile_max(n_valid));
         const bool need = (m_new - m_used) * c > 8.f;
         if (j > 0 && __any_sync(0xffffffffu, need)) {
           const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+          wait_pv(j);
           rescale_o(f);
           l_run *= f;
         }
         if (need) m_used = m_new;
       }
       float mx = -INFINITY;
-      float l_tile = tile_exp(n_valid, m_used, mx);
+      float l_tile = tile_exp(n_valid, m_used, mx, j);
       if (spec) {
         const float m_new = fmaxf(m_used, mx);
         const bool need = (m_new - m_used) * c > 8.f;
@@ -612,7 +632,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           rescale_o(f);
           l_run *= f;
           if (need) m_used = m_new;
-          l_tile = tile_exp(n_valid, m_used, mx);
+          l_tile = tile_exp(n_valid, m_used, mx, j);
         }
       }
       l_run += l_tile;
@@ -1170,6 +1190,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t st_tmem = tmem_base, dp_tmem = tmem_base + 128, dv_tmem = tmem_base + 256,
                  dk_tmem = tmem_base + 256 + p.dpad;
   auto dq_tmem = [&](int s) { return tmem_base + 256 + (2 + s) * p.dpad; };
+  // (dS^T as a second TMEM A operand, for dK, was measured SLOWER - 0.867 -> 1.02 ms at B8 N4096 d40: the extra TMEM
+  // reads of the MMA collide with the compute warps' tcgen05.ld / st traffic; dK and dQ read dS^T from shared memory)
 
   if (warp == 12) {
     // ===================== TMA producer =====================
@@ -1305,6 +1327,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool row_ok = kv0 + row < p.M;
     const uint64_t c2 = pack2(p.scale_log2, p.scale_log2), scale2 = pack2(p.scale, p.scale);
+    const float rowbias = row_ok ? 0.f : -INFINITY;
+    const uint64_t rowbias2 = pack2(rowbias, rowbias);
     const int rx = row & 7;
     for (int i = 0; i < TQ; ++i) {
       const int st = i & 1;
@@ -1329,11 +1353,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 nl = nlv[j >> 2];
+          // rows past M (last key tile only) get -inf added: P = 0 there
+          const uint64_t ta = fadd2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(nl.x, nl.y)), rowbias2);
+          const uint64_t tb = fadd2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), rowbias2);
+          // (the FMA-pipe polynomial that helps the forward was measured slower here - 0.867 -> 0.925 ms: these warps
+          // already fill the FMA pipe with the dS arithmetic - so every exponential goes to the MUFU pipe)
           float t0, t1, t2, t3;
-          unpack2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(nl.x, nl.y)), t0, t1);
-          unpack2(ffma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), c2, pack2(nl.z, nl.w)), t2, t3);
-          float p0 = ex2f(t0), p1 = ex2f(t1), p2 = ex2f(t2), p3 = ex2f(t3);
-          if (!row_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+          unpack2(ta, t0, t1);
+          unpack2(tb, t2, t3);
+          const float p0 = ex2f(t0), p1 = ex2f(t1), p2 = ex2f(t2), p3 = ex2f(t3);
           pk[j >> 1] = pack_bf16(p0, p1);
           pk[(j >> 1) + 1] = pack_bf16(p2, p3);
           ps2[half * 16 + (j >> 1)] = fmul2(pack2(p0, p1), scale2);
