@@ -180,6 +180,17 @@ int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, v
                      float ema_beta, float weight_decay, void* stream);
 int sidlsg_ema_update(const float* p, float* ema, long n, float beta, void* stream);
 
+/* ---- 4-channel 3x3 convolutions (conv_in / conv_out) as tensor-core GEMMs: data-movement helpers (bf16) ------------
+ * im2col of the NARROW tensor: col[p][k] = x[p + sign*off(tap)][c], k = tap*Cs + c (layout 0) or c*9 + tap (layout 1),
+ * col is [B*H*W, 64]; col2im: y[p][c] = bias[c] + sum_tap col[p + sign*off(tap)][k(tap,c)]; pad2d: zero-padded 2-D copy;
+ * add_transposed: dst[k][r] += src[r][k] (fp32).  The contractions are sidlsg_gemm calls (sid_lsg_b200/ops.py).
+ * ref: UNet2DConditionModel.conv_in / conv_out behind training/sid_sd_util.py:184,245,263. */
+int sidlsg_narrow_im2col(const void* x, void* col, int B, int H, int W, int Cs, int sign, int layout, void* stream);
+int sidlsg_narrow_col2im(const void* col, int ld, void* y, const float* bias, int B, int H, int W, int Cs,
+                         int sign, int layout, void* stream);
+int sidlsg_pad2d(const void* src, long lds, void* dst, int R, int K, int Rp, int Kp, void* stream);
+int sidlsg_add_transposed(const float* src, int lds, float* dst, int R, int K, void* stream);
+
 /* development aid: attention forward (d <= 64) with in-kernel clock64 stamps (32 x 16 long long, device memory) */
 int sidlsg_debug_attention_fwd_trace(const void* q, const void* k, const void* v, void* o, float* lse, int B,
                                      int N, int M, int H, int d, long ldq, long ldk, long ldv, void* trace,

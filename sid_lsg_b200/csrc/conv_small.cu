@@ -175,6 +175,83 @@ conv_small_wgrad_kernel(const T* __restrict__ wide, const T* __restrict__ narrow
     }
 }
 
+
+// =====================================================================================================================
+// The same two layers on the TENSOR CORES (bf16 mode): a 4-channel 3x3 convolution is a GEMM with K = 36 (or N = 36)
+// once the narrow tensor's 3x3 windows are written out ("im2col": 9 * Cs <= 64 values per pixel, 33 MB for 64 x 64 x 64
+// pixels) - the direct kernels above spend ~400 instructions per 16-byte store and ran 10-16x above the HBM time of the
+// wide tensor (conv_in forward 538 us, conv_out forward 601 us, their weight gradients 700 us per call at n = 32).
+// These helpers do the data movement; the contractions themselves are sidlsg_gemm calls composed in ops.py.
+//   off(tap) = (tap / 3 - 1, tap % 3 - 1);  k(tap, c) = tap * Cs + c  (layout 0)  or  c * 9 + tap  (layout 1)
+// col[p][k(tap, c)] = x[p + sign * off(tap)][c]   (0 outside the image; columns >= 9 * Cs zero), col is [M, 64] bf16
+__global__ void __launch_bounds__(256)
+narrow_im2col_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int B, int H, int W, int Cs, int sign, int layout) {
+  const long npix = (long)B * H * W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;    // one thread = one pixel x one 8-column piece
+  if (idx >= npix * 8) return;
+  const long pix = idx >> 3;
+  const int piece = (int)(idx & 7);
+  const int ox = (int)(pix % W);
+  const long r = pix / W;
+  const int oy = (int)(r % H);
+  const long b = r / H;
+  uint4 out;
+  bf16* o = reinterpret_cast<bf16*>(&out);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = piece * 8 + j;
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (k < 9 * Cs) {
+      const int tap = layout ? k % 9 : k / Cs, c = layout ? k / 9 : k % Cs;
+      const int iy = oy + sign * (tap / 3 - 1), ix = ox + sign * (tap % 3 - 1);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((b * H + iy) * W + ix) * Cs + c];
+    }
+    o[j] = v;
+  }
+  *reinterpret_cast<uint4*>(col + pix * 64 + piece * 8) = out;
+}
+
+// y[p][c] = bias[c] + sum_tap col[p + sign * off(tap)][k(tap, c)]     (col [M, ld] bf16, y [M, Cs] bf16 or fp32 NCHW-free)
+__global__ void __launch_bounds__(256)
+narrow_col2im_kernel(const bf16* __restrict__ col, int ld, bf16* __restrict__ y, const float* __restrict__ bias, int B, int H,
+                     int W, int Cs, int sign, int layout) {
+  const long npix = (long)B * H * W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;    // one thread = one pixel x one channel
+  if (idx >= npix * Cs) return;
+  const long pix = idx / Cs;
+  const int c = (int)(idx - pix * Cs);
+  const int ox = (int)(pix % W);
+  const long r = pix / W;
+  const int oy = (int)(r % H);
+  const long b = r / H;
+  float acc = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = oy + sign * (tap / 3 - 1), ix = ox + sign * (tap % 3 - 1);
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    acc += to_f(col[((b * H + iy) * W + ix) * ld + (layout ? c * 9 + tap : tap * Cs + c)]);
+  }
+  y[idx] = __float2bfloat16_rn(acc);
+}
+
+// dst [Rp, Kp] = zero-padded copy of src [R, K] (row stride lds); bf16
+__global__ void __launch_bounds__(256)
+pad2d_kernel(const bf16* __restrict__ src, long lds, bf16* __restrict__ dst, int R, int K, int Rp, int Kp) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Rp * Kp) return;
+  const int r = (int)(idx / Kp), k = (int)(idx - (long)r * Kp);
+  dst[idx] = (r < R && k < K) ? src[(long)r * lds + k] : __float2bfloat16_rn(0.f);
+}
+
+// dst[k][r] += src[r][k]   (src [R, lds] fp32, first K columns; dst [K, R] fp32)
+__global__ void __launch_bounds__(256)
+add_transposed_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int R, int K) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)R * K) return;
+  const int k = (int)(idx / R), r = (int)(idx - (long)k * R);
+  dst[idx] += src[(long)r * lds + k];
+}
+
 // returns 1 if handled, 0 if not eligible, <0 on error
 int conv_small_try(const void* x, const void* w, void* y, const float* bias, const void* res, const float* rowvec, int B,
                    int Hi, int Wi, int Kc, int Ho, int Wo, int N, long w_sn, long w_stap, long w_sk, int stride, int up,
@@ -237,3 +314,37 @@ int conv_small_wgrad_try(const void* x, const void* dy, float* dw, int B, int Hi
 }
 
 }  // namespace sidlsg
+
+using namespace sidlsg;
+
+// ---- data-movement helpers of the tensor-core form of the 4-channel convolutions (see narrow_im2col_kernel) ----------
+extern "C" int sidlsg_narrow_im2col(const void* x, void* col, int B, int H, int W, int Cs, int sign, int layout,
+                                    void* stream) {
+  if (Cs < 1 || 9 * Cs > 64) { set_error("narrow_im2col: Cs=%d", Cs); return SIDLSG_ERR_ARG; }
+  const long n = (long)B * H * W * 8;
+  if (n == 0) return SIDLSG_OK;
+  narrow_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)col, B, H, W,
+                                                                                       Cs, sign, layout);
+  return check_launch("narrow_im2col");
+}
+extern "C" int sidlsg_narrow_col2im(const void* col, int ld, void* y, const float* bias, int B, int H, int W, int Cs,
+                                    int sign, int layout, void* stream) {
+  if (Cs < 1 || 9 * Cs > ld) { set_error("narrow_col2im: Cs=%d ld=%d", Cs, ld); return SIDLSG_ERR_ARG; }
+  const long n = (long)B * H * W * Cs;
+  if (n == 0) return SIDLSG_OK;
+  narrow_col2im_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)col, ld, (bf16*)y, bias,
+                                                                                       B, H, W, Cs, sign, layout);
+  return check_launch("narrow_col2im");
+}
+extern "C" int sidlsg_pad2d(const void* src, long lds, void* dst, int R, int K, int Rp, int Kp, void* stream) {
+  const long n = (long)Rp * Kp;
+  if (n <= 0 || R > Rp || K > Kp) { set_error("pad2d: bad shape"); return SIDLSG_ERR_ARG; }
+  pad2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, lds, (bf16*)dst, R, K, Rp, Kp);
+  return check_launch("pad2d");
+}
+extern "C" int sidlsg_add_transposed(const float* src, int lds, float* dst, int R, int K, void* stream) {
+  const long n = (long)R * K;
+  if (n <= 0) return SIDLSG_OK;
+  add_transposed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, R, K);
+  return check_launch("add_transposed");
+}

@@ -166,6 +166,30 @@ def compute_weight(p, dtype):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# ---- conv_in / conv_out (a 4-channel side) as tensor-core GEMMs: im2col of the NARROW tensor + sidlsg_gemm --------------
+def _narrow_kind(x, C, N, stride, up, res, rowvec):
+    """'in' (few input channels), 'out' (few output channels) or None (general path); bf16 tensor-core mode only."""
+    if x.dtype != torch.bfloat16 or stride != 1 or up != 1:
+        return None
+    if 9 * C <= 64 and N >= 64 and N % 8 == 0:
+        return "in"
+    if 9 * N <= 48 and C >= 64 and C % 64 == 0 and res is None and rowvec is None:
+        return "out"
+    return None
+
+
+def _im2col(t, B, H, W, Cs, sign, layout):
+    col = torch.empty((B * H * W, 64), dtype=t.dtype, device=t.device)
+    lib.call("narrow_im2col", ptr(t), ptr(col), B, H, W, Cs, sign, layout, stream())
+    return col
+
+
+def _pad2d(src, R, K, Rp, Kp):
+    dst = torch.empty((Rp, Kp), dtype=src.dtype, device=src.device)
+    lib.call("pad2d", ptr(src), K, ptr(dst), R, K, Rp, Kp, stream())
+    return dst
+
+
 class Conv3x3Fn(Function):
     """3x3 convolution, padding 1, on x [B,H,W,C]; weight [N,C,3,3] stored channels_last (physical [N,3,3,C]).
     stride 2 = Downsample2D.conv; up 2 = Upsample2D (nearest 2x fused into the window gather);
@@ -186,7 +210,22 @@ class Conv3x3Fn(Function):
             rowvec = _c(rowvec)
             assert rowvec.dtype == torch.float32 and rowvec.shape == (B, N)
         ctx.split = _SPLIT[0] and x.dtype == torch.float32
+        ctx.narrow = _narrow_kind(x, C, N, stride, up, res, rowvec)
         done = False
+        M = B * H * W
+        if ctx.narrow == "in":
+            # y = im2col(x) [M, 64] . Wp^T: weights physically [N][3][3][C] = [N][9C] (k = tap*C + c), zero-padded to 64
+            col = _im2col(x, B, H, W, C, 1, 0)
+            wp = _pad2d(wc, N, 9 * C, N, 64)
+            gemm(col, 64, 1, wp, 64, 1, y, N, M, N, 64, bias=bias, res=res, ldr=N, rowvec=rowvec, rows_per_vec=H * W)
+            done = True
+        elif ctx.narrow == "out":
+            # ycol[p][(n, tap)] = x[p] . w[n][tap][:] (rows padded 9N -> 48), then y[p][n] = bias + sum_tap ycol[p + off(tap)]
+            wq = _pad2d(wc, 9 * N, C, 48, C)
+            ycol = torch.empty((M, 48), dtype=x.dtype, device=x.device)
+            gemm(x, C, 1, wq, C, 1, ycol, 48, M, 48, C)
+            lib.call("narrow_col2im", ptr(ycol), 48, ptr(y), ptr(bias), B, H, W, N, 1, 1, stream())
+            done = True
         if ctx.split and up == 1:
             ws, n = _split_ws(x.numel(), wc.numel(), x.device)
             done = lib.try_call("conv3x3_split3", ptr(x), ptr(wc), wc.numel(), ptr(y), ptr(bias), ptr(res), ptr(rowvec),
@@ -205,8 +244,11 @@ class Conv3x3Fn(Function):
         B, H, W, C, Ho, Wo, N, stride, up = ctx.geom
         dy = _c(dy)
         dx = None
+        if ctx.narrow is not None:
+            return Conv3x3Fn._backward_narrow(ctx, x, wc, dy)
         if ctx.needs_input_grad[0]:
             dfull = torch.empty((B, H * up, W * up, C), dtype=dy.dtype, device=dy.device)
+
             def dgrad_s1(g, Hg, Wg):
                 """stride-1 data gradient of g [B,Hg,Wg,N] -> dfull (tensor cores: bf16, or fp32 as three bf16 passes)"""
                 if ctx.split:
@@ -248,6 +290,45 @@ class Conv3x3Fn(Function):
             drow = torch.empty((B, N), dtype=torch.float32, device=dy.device)
             lib.call("colsum", ptr(dy), ptr(drow), B, Ho * Wo, N, 0, dt(dy), stream())
         return dx, None, None, None, (dy if ctx.needs_input_grad[4] else None), drow, None, None, None
+
+
+def _conv3x3_backward_narrow(ctx, x, wc, dy):
+    """data / weight / bias / row-vector gradients of the 4-channel convolutions, all contractions on tcgen05."""
+    B, H, W, C, Ho, Wo, N, stride, up = ctx.geom
+    M = B * H * W
+    dev = dy.device
+    dx = None
+    if ctx.narrow == "in":
+        if ctx.needs_input_grad[0]:
+            wp = _pad2d(wc, N, 9 * C, N, 64)
+            dcol = torch.empty((M, 64), dtype=dy.dtype, device=dev)
+            gemm(dy, N, 1, wp, 1, 64, dcol, 64, M, 64, N)                      # dcol = dy . Wp
+            dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dev)
+            lib.call("narrow_col2im", ptr(dcol), 64, ptr(dx), None, B, H, W, C, -1, 0, stream())
+        if ctx.needs_input_grad[1]:
+            col = _im2col(x, B, H, W, C, 1, 0)
+            # dW [N, 9C] += dy^T . col (fp32 atomics straight into the flat gradient bucket)
+            gemm(dy, 1, N, col, 1, 64, _grad_of(ctx.weight), 9 * C, N, 9 * C, M, accumulate=2, out_dtype=F32)
+    else:
+        dycol = _im2col(dy, B, H, W, N, -1, 1)                                   # dycol[q][(n, tap)] = dy[q - off(tap)][n]
+        if ctx.needs_input_grad[0]:
+            wq = _pad2d(wc, 9 * N, C, 64, C)
+            dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dev)
+            gemm(dycol, 64, 1, wq, 1, C, dx, C, M, C, 64)                       # dx = dycol . Wq
+        if ctx.needs_input_grad[1]:
+            tmp = torch.zeros((C, 64), dtype=torch.float32, device=dev)
+            gemm(x, 1, C, dycol, 1, 64, tmp, 64, C, 64, M, accumulate=2, out_dtype=F32)   # tmp[c][(n, tap)]
+            lib.call("add_transposed", ptr(tmp), 64, ptr(_grad_of(ctx.weight)), C, 9 * N, stream())
+    if ctx.bias is not None and ctx.needs_input_grad[3]:
+        lib.call("colsum", ptr(dy), ptr(_grad_of(ctx.bias)), 1, M, N, 1, dt(dy), stream())
+    drow = None
+    if ctx.needs_input_grad[5]:
+        drow = torch.empty((B, N), dtype=torch.float32, device=dev)
+        lib.call("colsum", ptr(dy), ptr(drow), B, H * W, N, 0, dt(dy), stream())
+    return dx, None, None, None, (dy if ctx.needs_input_grad[4] else None), drow, None, None, None
+
+
+Conv3x3Fn._backward_narrow = staticmethod(_conv3x3_backward_narrow)
 
 
 def conv3x3(x, weight, bias=None, res=None, rowvec=None, stride=1, up=1):

@@ -377,3 +377,42 @@ def test_split3_conv3x3_matches_fp64(B, H, C, N, stride):
     assert _relerr(yd.permute(0, 3, 1, 2), yr) < 3e-5, _relerr(yd.permute(0, 3, 1, 2), yr)
     assert _relerr(xd.grad.permute(0, 3, 1, 2), xr.grad) < 3e-5, _relerr(xd.grad.permute(0, 3, 1, 2), xr.grad)
     assert _relerr(wd.grad, wr.grad) < 3e-5, _relerr(wd.grad, wr.grad)
+
+
+@pytest.mark.parametrize("B,H,C,N,with_rv", [(2, 64, 4, 320, True), (3, 16, 4, 64, False), (2, 64, 320, 4, False),
+                                             (1, 32, 64, 4, False)])
+def test_narrow_conv_as_tensor_core_gemm(B, H, C, N, with_rv):
+    """conv_in (4 -> 320) / conv_out (320 -> 4) in bf16: im2col of the 4-channel tensor + tcgen05 GEMMs (ops.py
+    `_narrow_kind`), forward, data, weight, bias and timestep-row gradients vs fp32 torch; no CUDA-core GEMM runs."""
+    import ctypes
+    from sid_lsg_b200._lib import lib
+    g = torch.Generator().manual_seed(4)
+    x = bf(torch.randn(B, C, H, H, generator=g))
+    w = bf(torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    b = torch.randn(N, generator=g)
+    rv = torch.randn(B, N, generator=g)
+    xr, wr, br, rvr = (t.clone().requires_grad_(True) for t in (x, w, b, rv))
+    yr = F.conv2d(xr, wr, br, padding=1)
+    if with_rv:
+        yr = yr + rvr[:, :, None, None]
+    dy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(dy)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16().requires_grad_(True)
+    rvd = rv.to(DEV).requires_grad_(True)
+    wp = BfParam(w, channels_last=True)
+    bp = torch.nn.Parameter(b.to(DEV))
+    bp.grad = torch.zeros_like(bp)
+    c0 = (ctypes.c_long * 2)()
+    lib.query("counters", c0)
+    y = ops().conv3x3(xd, wp, bp, None, rvd if with_rv else None)
+    y.backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV).bfloat16())
+    torch.cuda.synchronize()
+    c1 = (ctypes.c_long * 2)()
+    lib.query("counters", c1)
+    assert c1[0] - c0[0] == 3 and c1[1] == c0[1], (list(c0), list(c1))      # fwd, dgrad, wgrad: three tcgen05 GEMMs
+    check(y.permute(0, 3, 1, 2), yr, 1.5e-2, "y")
+    check(xd.grad.permute(0, 3, 1, 2), xr.grad, 1.5e-2, "dx")
+    check(wp.grad, wr.grad, 3e-3, "dw")
+    check(bp.grad, br.grad, 3e-3, "dbias")
+    if with_rv:
+        check(rvd.grad, rvr.grad, 1e-2, "drowvec")
