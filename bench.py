@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (ncu launch-list captures only)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     ap.add_argument("--shapes", default=None, help="write the per-shape kernel table of the roofline step to this file")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the iteration as a CUDA graph in the timed regions "
+                                                         "(training.step.GraphedIteration), 0: eager launches")
     return ap.parse_args()
 
 
@@ -270,11 +272,35 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
+
+    # ---- roofline pass: one eager step with per-call CUDA events on the kernels' own stream (before the graph capture:
+    # events per call cannot live inside a captured graph, and the graph's memory pool should not sit beside the eager one)
+    peaks = load_peaks()
+    timer = None
+    if not args.no_roofline:
+        # every rank runs the extra step (it contains the gradient allreduces); only rank 0 instruments it
+        timer = KernelTimer() if rank == 0 else None
+        S.lib.timer = timer
+        step_resident(0, args.warmup)
+        torch.cuda.synchronize()
+        S.lib.timer = None
+
+    graphed = None
+    if args.graph:
+        f0, g0 = resident[args.warmup]
+        graphed = S.GraphedIteration(st, f0, g0, batch_size=args.batch * world)
+
+        def step_resident(i, off=0):  # noqa: F811
+            f, g = resident[off + i]
+            losses.append(graphed(f, g))
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     n0 = S.lib.launches
     ms_total = timed(lambda i: step_resident(i, args.warmup), args.steps)
     launches = S.lib.launches - n0
+    if graphed is not None:
+        launches = graphed.calls_per_replay * args.steps    # every replay re-issues the kernels of the captured C-ABI calls
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms_step = ms_total / args.steps
@@ -289,7 +315,7 @@ def main():
         f, g = host[args.warmup + i]
         fd = [to_device(m, dev) for m in f]
         gd = [to_device(m, dev) for m in g]
-        lf, lg = st.iteration(fd, gd, batch_size=args.batch * world)
+        lf, lg = graphed(fd, gd) if graphed is not None else st.iteration(fd, gd, batch_size=args.batch * world)
         loss_host[:2].copy_(lf, non_blocking=True)
         loss_host[2:].copy_(lg, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the loop reads the losses every iteration (:452, :535)
@@ -308,20 +334,13 @@ def main():
             "config": workload_config(args, world), "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 16},
-            "gpu_launches": launches, "losses_finite": finite,
+            "gpu_launches": launches, "launch_mode": ("cuda graph replay of the whole iteration (kernels per replay = "
+                                                      "gpu_launches / steps)" if graphed is not None else "eager"),
+            "losses_finite": finite,
             "loss_fake": float(last_f[0].item()), "loss_G": float(last_g[0].item()),
             "step_tflops_algorithmic": STEP_FLOPS_PER_IMAGE * args.batch / (ms_step / 1e3) / 1e12 if args.model == "SD15" else None,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
 
-    # ---- roofline pass: one more step with per-call CUDA events on the kernels' own stream ---------------------
-    peaks = load_peaks()
-    if not args.no_roofline:
-        # every rank runs the extra step (it contains the gradient allreduces); only rank 0 instruments it
-        timer = KernelTimer() if rank == 0 else None
-        S.lib.timer = timer
-        step_resident(0, args.warmup)
-        torch.cuda.synchronize()
-        S.lib.timer = None
     if rank == 0 and not args.no_roofline:
         summ = timer.summary()
         kern = {}
@@ -348,7 +367,7 @@ def main():
                             "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                             "launches": n, "avg_launch_ms": round(ms / max(n, 1), 4),
                             "algorithmic_flop_per_launch": work / max(n, 1), "share_of_step": round(ms / ms_step, 4),
-                            "measured_on": "1 instrumented step right after the timed region (per-call CUDA events on the launch stream)",
+                            "measured_on": "1 instrumented eager step right before the timed region (per-call CUDA events on the launch stream)",
                             "limiter": "L2->SM operand delivery, 42-47 B/clk/SM in ncu (l1tex__m_xbar2l1tex_read_bytes; profiles/r01_ncu_conv_*.txt): 256-row tiles cut bytes per FLOP 1.4-1.5x; the FLOP roofline is reported because the contract offers hbm|tensor"}
         line["kernels"] = kern
         if args.shapes:

@@ -172,13 +172,19 @@ int sidlsg_lsg_loss(const float* xg, const float* yreal, const float* yfake, flo
  * g <- nan_to_num(g * grad_scale, 0, 1e5, -1e5) [clip to +-clip if clip > 0]; Adam(beta1, beta2, eps) with
  * torch.optim.Adam bias correction at `step`; optional decoupled weight decay; optional EMA
  * ema <- p + ema_beta (ema - p) after the step; optional bf16 shadows of p and of ema (the copies the tensor-core
- * GEMMs of G and G_ema read). m may be null when beta1 == 0.
+ * GEMMs of G and G_ema read).  hyper (optional, device float[4] {lr, 1-beta1^step, sqrt(1-beta2^step), ema_beta}) overrides
+ * the scalar arguments at run time, so a captured launch (CUDA graph) follows the step count. m may be null when beta1 == 0.
  * ref: training/sid_training_loop.py:458-462, 541-549, 553-565; sid_train.py:219-226. */
 int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
                      void* ema_shadow_bf16, long n,
                      float lr, float beta1, float beta2, float eps, int step, float grad_scale, float clip,
-                     float ema_beta, float weight_decay, void* stream);
+                     float ema_beta, float weight_decay, const float* hyper, void* stream);
 int sidlsg_ema_update(const float* p, float* ema, long n, float beta, void* stream);
+/* Advances device-side counters {Adam steps f_psi, Adam steps G_theta, images seen} and writes the per-step scalars of
+ * both optimiser passes (hyper[8], see sidlsg_adam_step) - the first node of a captured iteration (CUDA graph).
+ * rampup < 0 = no EMA ramp-up.  ref: training/sid_training_loop.py:553-558, torch.optim.Adam bias corrections. */
+int sidlsg_hyper_advance(float* hyper, long long* counters, float lr, float glr, float beta1, float beta2,
+                         double batch, double halflife_nimg, double rampup, int ema_on, void* stream);
 
 /* ---- 4-channel 3x3 convolutions (conv_in / conv_out) as tensor-core GEMMs: data-movement helpers (bf16) ------------
  * im2col of the NARROW tensor: col[p][k] = x[p + sign*off(tap)][c], k = tap*Cs + c (layout 0) or c*9 + tap (layout 1),

@@ -10,7 +10,7 @@ from . import torch_utils, dnnlib  # noqa: F401
 from .training.sid_sd_util import sid_sd_sampler, sid_sd_denoise, PromptBatch, load_sd15  # noqa: F401
 from .training.sid_training_loop import training_loop  # noqa: F401
 from .training.draws import DrawStream  # noqa: F401
-from .training.step import SiDLSGStep, synth_microbatch, device_microbatch, ema_beta  # noqa: F401
+from .training.step import SiDLSGStep, GraphedIteration, synth_microbatch, device_microbatch, ema_beta  # noqa: F401
 from .training.prompts import PromptEncoder  # noqa: F401
 from .training import checkpoint  # noqa: F401
 from .training.checkpoint import load_unet, save_unet, save_network_snapshot, load_network_snapshot  # noqa: F401

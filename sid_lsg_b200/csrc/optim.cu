@@ -20,6 +20,8 @@ struct AdamArgs {
   bf16* ema_shadow;  // null: the EMA network keeps no bf16 shadow
   long n;
   float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, clip, ema_beta, weight_decay;
+  const float* hyper;   // optional device float[4] {lr, bc1, bc2_sqrt, ema_beta} read at run time (CUDA-graph replay: the
+                        // per-step scalars must not be baked into the captured launch)
 };
 
 __device__ __forceinline__ float sanitize(float g) {
@@ -29,6 +31,10 @@ __device__ __forceinline__ float sanitize(float g) {
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+  if (a.hyper) {
+    const float4 h = *reinterpret_cast<const float4*>(a.hyper);
+    a.lr = h.x; a.bc1 = h.y; a.bc2_sqrt = h.z; a.ema_beta = h.w;
+  }
   const long nvec = a.n >> 2;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -87,15 +93,43 @@ __global__ void __launch_bounds__(256) ema_kernel(const float* __restrict__ p, f
   }
 }
 
+// Per-step scalars of the two optimiser passes computed ON THE DEVICE from device-side counters, so a captured iteration
+// (CUDA graph) advances its own step count: counters = {Adam steps of f_psi, Adam steps of G_theta, images seen}.
+// hyper[0..3] = f_psi {lr, 1 - b1^t, sqrt(1 - b2^t), 0};  hyper[4..7] = G_theta {glr, ..., ..., ema_beta}
+// (EMA beta as training/sid_training_loop.py:553-558: 0.5^(batch / max(min(halflife, nimg * rampup), 1e-8))).
+__global__ void hyper_advance_kernel(float* hyper, long long* counters, float lr, float glr, float beta1, float beta2,
+                                     double batch, double halflife_nimg, double rampup, int ema_on) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long tf = ++counters[0], tg = ++counters[1], nimg = counters[2];
+  hyper[0] = lr;
+  hyper[1] = (float)(1.0 - pow((double)beta1, (double)tf));
+  hyper[2] = (float)sqrt(1.0 - pow((double)beta2, (double)tf));
+  hyper[3] = 0.f;
+  hyper[4] = glr;
+  hyper[5] = (float)(1.0 - pow((double)beta1, (double)tg));
+  hyper[6] = (float)sqrt(1.0 - pow((double)beta2, (double)tg));
+  double half = halflife_nimg;
+  if (rampup >= 0.0) half = fmin(half, (double)nimg * rampup);
+  hyper[7] = ema_on ? (float)pow(0.5, batch / fmax(half, 1e-8)) : 0.f;
+  counters[2] = nimg + (long long)batch;
+}
+
 }  // namespace sidlsg
 
 using namespace sidlsg;
+
+extern "C" int sidlsg_hyper_advance(float* hyper, long long* counters, float lr, float glr, float beta1, float beta2,
+                                    double batch, double halflife_nimg, double rampup, int ema_on, void* stream) {
+  hyper_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, counters, lr, glr, beta1, beta2, batch, halflife_nimg,
+                                                           rampup, ema_on);
+  return check_launch("hyper_advance");
+}
 
 // n must be a multiple of 4 (the flat bucket is padded).  step >= 1 is the Adam step count AFTER this update.
 extern "C" int sidlsg_adam_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
                                 void* ema_shadow_bf16, long n,
                                 float lr, float beta1, float beta2, float eps, int step, float grad_scale, float clip,
-                                float ema_beta, float weight_decay, void* stream) {
+                                float ema_beta, float weight_decay, const float* hyper, void* stream) {
   if (n % 4) { set_error("adam_step: n=%ld not a multiple of 4", n); return SIDLSG_ERR_ARG; }
   if (step < 1) { set_error("adam_step: step must be >= 1"); return SIDLSG_ERR_ARG; }
   if (beta1 != 0.f && !m) { set_error("adam_step: beta1 != 0 needs the m buffer"); return SIDLSG_ERR_ARG; }
@@ -107,6 +141,7 @@ extern "C" int sidlsg_adam_step(float* p, const float* g, float* m, float* v, fl
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.grad_scale = grad_scale; a.clip = clip; a.ema_beta = ema_beta; a.weight_decay = weight_decay;
+  a.hyper = hyper;
   long nvec = n / 4;
   int blocks = (int)min((long)148 * 8, (nvec + 255) / 256);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);

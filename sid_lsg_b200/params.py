@@ -102,8 +102,13 @@ class FlatParams:
             return dist.all_reduce(self.ensure_grad(), op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         return None
 
+    @staticmethod
+    def adam_hyper(lr, betas, step, ema_beta=0.0):
+        """the four per-step scalars of the fused optimiser pass (what sidlsg_adam_step derives from its arguments)"""
+        return (float(lr), 1.0 - betas[0] ** step, (1.0 - betas[1] ** step) ** 0.5, float(ema_beta))
+
     def adam_step(self, lr, betas=(0.0, 0.999), eps=1e-8, grad_scale=1.0, clip=0.0, ema=None, ema_beta=0.0,
-                  weight_decay=0.0):
+                  weight_decay=0.0, hyper=None):
         """nan_to_num + clip + Adam (+ EMA into `ema`, another FlatParams' master) (+ bf16 shadow), one launch."""
         if self.exp_avg_sq is None:
             self.init_adam(betas[0])
@@ -114,7 +119,7 @@ class FlatParams:
                  ptr(ema.master) if ema is not None else None, ptr(self.shadow),
                  ptr(ema.shadow) if ema is not None else None, self.numel,
                  float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, float(grad_scale),
-                 float(clip), float(ema_beta), float(weight_decay), stream())
+                 float(clip), float(ema_beta), float(weight_decay), ptr(hyper), stream())
 
     def ema_into(self, ema, beta):
         lib.call("ema_update", ptr(self.master), ptr(ema.master), self.numel, float(beta), stream())

@@ -36,7 +36,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     """Argument validation happens before any launch: status < 0 and a message, RuntimeError in Python."""
     from sid_lsg_b200._lib import lib
     with pytest.raises(RuntimeError, match="adam_step"):
-        lib.call("adam_step", None, None, None, None, None, None, None, 6, 1e-3, 0.0, 0.999, 1e-8, 1, 1.0, 0.0, 0.0, 0.0, None)
+        lib.call("adam_step", None, None, None, None, None, None, None, 6, 1e-3, 0.0, 0.999, 1e-8, 1, 1.0, 0.0, 0.0, 0.0, None, None)
     with pytest.raises(RuntimeError, match="CHW"):
         lib.call("lsg_loss", None, None, None, None, None, None, None, 1, 7, 1.0, 1.0, None)
 
