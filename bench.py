@@ -363,7 +363,8 @@ def main():
         ach = work / (ms / 1e3) / 1e12 if ms > 0 else 0.0
         line["roofline"] = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv3x3: linear+conv fwd, dgrad, wgrad)",
                             "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tflops_sustained"],
-                            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": load_traffic(),
+                            "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
+                            "traffic": (load_traffic() or {}).get("dram_bytes"), "traffic_detail": load_traffic(),
                             "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                             "launches": n, "avg_launch_ms": round(ms / max(n, 1), 4),
                             "algorithmic_flop_per_launch": work / max(n, 1), "share_of_step": round(ms / ms_step, 4),
