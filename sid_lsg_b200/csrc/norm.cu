@@ -101,11 +101,21 @@ gn_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
+  // a lane owns whole chunks (its cpg channels are contiguous: no index division, loads issued back to back with two
+  // independent accumulator pairs) - the previous element-strided loop was a chain of 20 dependent L2 round trips and
+  // made this 10-25 us of pure latency per GroupNorm call
   double s = 0, q = 0;
-  for (int i = lane; i < chunks * cpg; i += 32) {
-    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
-    const float2 v = partial[((long)b * chunks + ch) * C + c];
-    s += v.x; q += v.y;
+  for (int ch = lane; ch < chunks; ch += 32) {
+    const float2* pp = partial + ((long)b * chunks + ch) * C + g * cpg;
+    double s0 = 0, q0 = 0, s1 = 0, q1 = 0;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 1 < cpg; j += 2) {
+      const float2 v0 = pp[j], v1 = pp[j + 1];
+      s0 += v0.x; q0 += v0.y; s1 += v1.x; q1 += v1.y;
+    }
+    if (j < cpg) { const float2 v0 = pp[j]; s0 += v0.x; q0 += v0.y; }
+    s += s0 + s1; q += q0 + q1;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
@@ -253,11 +263,19 @@ gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restri
   if (w >= B * G) return;
   const int b = w / G, g = w - b * G, cpg = C / G;
   double S1 = 0, S2 = 0;
-  for (int i = lane; i < chunks * cpg; i += 32) {
-    const int ch = i / cpg, c = g * cpg + (i - ch * cpg);
-    const float2 v = partial[((long)b * chunks + ch) * C + c];
-    const double ga = gamma[c];
-    S1 += ga * v.x; S2 += ga * v.y;
+  for (int ch = lane; ch < chunks; ch += 32) {       // lane = chunk, as in gn_finalize_kernel
+    const float2* pp = partial + ((long)b * chunks + ch) * C + g * cpg;
+    const float* gp = gamma + g * cpg;
+    double a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 1 < cpg; j += 2) {
+      const float2 v0 = pp[j], v1 = pp[j + 1];
+      const double g0 = gp[j], g1 = gp[j + 1];
+      a0 += g0 * v0.x; b0 += g0 * v0.y; a1 += g1 * v1.x; b1 += g1 * v1.y;
+    }
+    if (j < cpg) { const float2 v0 = pp[j]; const double g0 = gp[j]; a0 += g0 * v0.x; b0 += g0 * v0.y; }
+    S1 += a0 + a1; S2 += b0 + b1;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { S1 += __shfl_xor_sync(0xffffffffu, S1, o); S2 += __shfl_xor_sync(0xffffffffu, S2, o); }

@@ -46,7 +46,8 @@ class BfParam:
 
 
 @pytest.mark.parametrize("M,K,N", [(256, 64, 64), (4096, 320, 320), (1000, 768, 640), (512, 1280, 2560), (300, 640, 136),
-                                   (8192, 320, 960), (24576, 320, 320), (640, 320, 96), (384, 128, 80), (2048, 1280, 1280)])
+                                   (8192, 320, 960), (24576, 320, 320), (640, 320, 96), (384, 128, 80), (2048, 1280, 1280),
+                                   (16384, 640, 320), (9000, 320, 2560), (8192, 384, 136)])
 def test_tc_linear(M, K, N):
     g = torch.Generator().manual_seed(0)
     x = bf(torch.randn(M, K, generator=g))
