@@ -427,8 +427,16 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down order matters: a CUDA graph that captured NCCL collectives must be gone before the communicator is,
+        # and destroying the communicator after graph-captured collectives was seen to hang (N = 2, NCCL 2.28.9): the
+        # line is out, every rank has passed the barrier, so the processes simply exit.
+        if graphed is not None:
+            graphed.graph.reset()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
