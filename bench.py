@@ -382,6 +382,10 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del resident
+        if graphed is not None:              # the captured iteration owns ~100 GB of activations in its private pool
+            graphed.graph.reset()
+            graphed.static_f = graphed.static_g = graphed.out = None
+        losses.clear()
         torch.cuda.empty_cache()
         del st, true_score, fake, G, G_ema, base
         import gc
