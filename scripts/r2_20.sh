@@ -1,0 +1,5 @@
+#!/bin/bash
+OUT=gpurun_out/r2w; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_tc_gpu.py -m gpu -q -x -p no:cacheprovider -k attention 2>&1 | tail -2
+SIDLSG_ATTN_FWD4=0 timeout 300 python scripts/micro.py attn 10 2>&1 | grep -A1 "attn fwd" | tee $OUT/micro.txt
+timeout 120 python scripts/trace_attn_bwd.py > $OUT/trace_bwd2.txt 2>&1; cut -c1-200 $OUT/trace_bwd2.txt | tail -8

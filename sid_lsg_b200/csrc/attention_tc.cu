@@ -440,6 +440,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_expect_tx(q_full(x), AT_CHUNK);
         tma_load_4d(&tmQ, q_full(x), q_smem + x * AT_CHUNK, 0, h, q0 + x * AT_BQ, b);
       }
+#pragma unroll 1
       for (int j = 0; j < T; ++j) {
         const int ks = j % A3_KST, vs = j % A3_VST;
         mbar_wait_h(p.wait_hint, k_empty(ks), ((j / A3_KST) & 1) ^ 1);
@@ -452,48 +453,89 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
+    // One thread, one long dependent instruction stream: at ~3,000 clk per key tile it WAS the period of the kernel
+    // (phase trace r02: every wait on an already-complete barrier cost 150-250 clk - two constant-bank loads, a uniform
+    // compare and the try_wait in series - and every MMA ~55 clk of dependent uniform-datapath descriptor arithmetic,
+    // while the tensor pipe needs ~1,700 clk).  So: the suspend hint lives in a register, descriptors are base + immediate
+    // (independent adds, loops fully unrolled with predicates), and nothing but the fence sits between seeing P_X(j)
+    // and issuing S_X(j + 1).
     if (role_leader()) {
+      uint32_t hint;
+      asm volatile("mov.u32 %0, %1;" : "=r"(hint) : "r"(p.wait_hint));
+      auto wait = [&](uint32_t bar, uint32_t parity) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok) mbar_wait_h(hint, bar, parity);
+      };
       const int dsteps = p.dpad >> 4;
       const uint32_t idesc_pv = make_idesc(p.dpad, 0, 1);
-      auto issue_qk = [&](int x, int j) {
-        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
-        const uint32_t idesc = make_idesc((n_valid + 15) & ~15, 0, 0);
-        const uint32_t kb = k_smem + (j % A3_KST) * AT_CHUNK, qb = q_smem + x * AT_CHUNK;
-        for (int s2 = 0; s2 < dsteps; ++s2)
-          tc_mma_bf16(s_tmem(x), make_desc(qb + s2 * 32, 1024, 0), make_desc(kb + s2 * 32, 1024, 0), idesc, s2 > 0);
-        tc_commit(s_full(x));
+      const uint32_t idesc_full = make_idesc(AT_BKV, 0, 0);
+      const int n_last = p.M - (T - 1) * AT_BKV;
+      const uint32_t idesc_last = make_idesc((n_last + 15) & ~15, 0, 0);
+      const int ksteps_last = (n_last + 15) >> 4;
+      const uint64_t qd0 = make_desc(q_smem, 1024, 0), qd1 = make_desc(q_smem + AT_CHUNK, 1024, 0);
+      const uint64_t kd0 = make_desc(k_smem, 1024, 0), vd0 = make_desc(v_smem, 1024, AT_CHUNK);
+      const uint32_t s0 = s_tmem(0), s1 = s_tmem(1), o0 = o_tmem(0), o1 = o_tmem(1), p0 = p_tmem(0), p1 = p_tmem(1);
+      const bool two = ntile == 2;
+      // S_X = Q_X K^T: <= 4 MMAs of K = 16 (descriptor + 2 = 32 bytes along the 128-byte swizzled row)
+      auto issue_qk = [&](uint32_t st, uint64_t qd, uint64_t kd, uint32_t idesc, uint32_t bar) {
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2)
+          if (s2 < dsteps) tc_mma_bf16(st, qd + 2 * s2, kd + 2 * s2, idesc, s2 > 0);
+        tc_commit(bar);
       };
-      for (int x = 0; x < ntile; ++x) mbar_wait_h(p.wait_hint, q_full(x), 0);
-      mbar_wait_h(p.wait_hint, k_full(0), 0);
+      // O_X += P_X V: <= 8 MMAs of K = 16 keys (P from TMEM, 8 columns each; V rows 16 s2 .. = + 2,048 bytes)
+      auto issue_pv = [&](uint32_t ot, uint32_t pt, uint64_t vd, int ksteps, uint32_t acc0, uint32_t bar) {
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2)
+          if (s2 < ksteps) tc_mma_bf16_ta(ot, pt + 8 * s2, vd + 128 * s2, idesc_pv, s2 > 0 ? 1u : acc0);
+        tc_commit(bar);
+      };
+      wait(q_full(0), 0);
+      if (two) wait(q_full(1), 0);
+      wait(k_full(0), 0);
       tc_fence_after();
-      for (int x = 0; x < ntile; ++x) issue_qk(x, 0);
+      {
+        const uint32_t id0 = T == 1 ? idesc_last : idesc_full;
+        issue_qk(s0, qd0, kd0, id0, s_full(0));
+        if (two) issue_qk(s1, qd1, kd0, id0, s_full(1));
+      }
       tc_commit(k_empty(0));
+#pragma unroll 1
       for (int j = 0; j < T; ++j) {
-        const int vs = j % A3_VST;
-        const int n_valid = min(AT_BKV, p.M - j * AT_BKV);
-        const int ksteps = (n_valid + 15) >> 4;
-        const uint32_t vb = v_smem + vs * AT_CHUNK;
+        const int vs = j & (A3_VST - 1), ks = (j + 1) & (A3_KST - 1);
         const bool more = j + 1 < T;
+        const int ksteps = more ? AT_BKV / 16 : ksteps_last;
+        const uint32_t idq = (j + 2 < T) ? idesc_full : idesc_last;
+        const uint64_t vd = vd0 + (uint64_t)(vs * (AT_CHUNK >> 4)), kd = kd0 + (uint64_t)(ks * (AT_CHUNK >> 4));
+        const uint32_t acc0 = j > 0 ? 1u : 0u, par = j & 1;
         const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
-        mbar_wait_h(p.wait_hint, v_full(vs), (j / A3_VST) & 1);
-        if (more) mbar_wait_h(p.wait_hint, k_full((j + 1) % A3_KST), ((j + 1) / A3_KST) & 1);
-        for (int x = 0; x < ntile; ++x) {
-          if (tr) p.trace[j * 16 + 8 + 3 * x] = clock64();
-          mbar_wait_h(p.wait_hint, p_full(x), j & 1);
-          if (tr) p.trace[j * 16 + 9 + 3 * x] = clock64();
+        if (tr) p.trace[j * 16 + 14] = clock64();
+        if (more) wait(k_full(ks), ((j + 1) >> 2) & 1);
+        if (tr) p.trace[j * 16 + 8] = clock64();
+        wait(p_full(0), par);
+        if (tr) p.trace[j * 16 + 9] = clock64();
+        tc_fence_after();
+        // S_X(j) has been consumed (P_X(j) exists): the NEXT tile's scores go first, so the softmax warps get them
+        // right away instead of after the 8 MMAs of P V (their exponentials of tile j + 1 then run under P_X(j) V_j;
+        // they wait on o_full before touching P_X or O_X again)
+        if (more) issue_qk(s0, qd0, kd, idq, s_full(0));
+        if (tr) p.trace[j * 16 + 7] = clock64();
+        wait(v_full(vs), (j >> 2) & 1);
+        issue_pv(o0, p0, vd, ksteps, acc0, o_full(0));
+        if (tr) p.trace[j * 16 + 10] = clock64();
+        if (two) {
+          if (tr) p.trace[j * 16 + 11] = clock64();
+          wait(p_full(1), par);
+          if (tr) p.trace[j * 16 + 12] = clock64();
           tc_fence_after();
-          // S_X(j) has been consumed (P_X(j) exists): the NEXT tile's scores go first, so the softmax warps get them
-          // ~330 clk after their arrival instead of after the 8 + 3 MMAs of P V and Q K^T (their exponentials of tile
-          // j + 1 then run under P_X(j) V_j; they wait on o_full before touching P_X or O_X again)
-          if (more) issue_qk(x, j + 1);
-          for (int s2 = 0; s2 < ksteps; ++s2)
-            tc_mma_bf16_ta(o_tmem(x), p_tmem(x) + s2 * 8, make_desc(vb + s2 * 2048, 1024, AT_CHUNK), idesc_pv,
-                           (j > 0 || s2 > 0) ? 1u : 0u);
-          tc_commit(o_full(x));
-          if (tr) p.trace[j * 16 + 10 + 3 * x] = clock64();
+          if (more) issue_qk(s1, qd1, kd, idq, s_full(1));
+          issue_pv(o1, p1, vd, ksteps, acc0, o_full(1));
+          if (tr) p.trace[j * 16 + 13] = clock64();
         }
         tc_commit(v_empty(vs));
-        if (more) tc_commit(k_empty((j + 1) % A3_KST));
+        if (more) tc_commit(k_empty(ks));
       }
     }
   } else if ((warp >> 2) < ntile) {
@@ -508,6 +550,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     auto tile_max = [&](int n_valid) {
       float mx = -INFINITY;
+#pragma unroll 1
       for (int cc = 0; cc < n_valid; cc += 32) {
         uint32_t r[32];
         tmem_ld32_nowait(st + cc, r);
@@ -566,6 +609,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         unpack2(ls2, a0, a1);
         ls = a0 + a1;
       } else {
+#pragma unroll 1
         for (int cc = 0; cc < n_valid; cc += 32) {
           uint32_t r[32], pk[16];
           tmem_ld32_nowait(st + cc, r);
@@ -589,6 +633,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       return ls;
     };
     auto rescale_o = [&](float f) {
+#pragma unroll 1
       for (int cc = 0; cc < p.dpad; cc += 16) {
         uint32_t r[16];
         tmem_ld16_nowait(ot + cc, r);
@@ -605,7 +650,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool spec = j > 0 && n_valid == AT_BKV;
       // S_X(j) is issued BEFORE P_X V_{j-1}: that product may still be running when the scores arrive, so O_X and the
       // P_X region are touched only after o_full (wait_pv below; by then most of the first 32 columns are done)
-      const bool tr = TRACE && (threadIdx.x & 127) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
+      const bool tr = TRACE && (warp & 3) == 0 && lane == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32;
       if (tr) p.trace[j * 16 + 4 * x] = clock64();
       mbar_wait(s_full(x), j & 1);
       if (tr) p.trace[j * 16 + 4 * x + 1] = clock64();
@@ -622,21 +667,25 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         if (need) m_used = m_new;
       }
-      float mx = -INFINITY;
-      float l_tile = tile_exp(n_valid, m_used, mx, j);
-      if (spec) {
+      float l_tile;
+#pragma unroll 1
+      for (int pass = 0;; ++pass) {                // (a loop so that the exponential code exists once: I-cache)
+        float mx = -INFINITY;
+        l_tile = tile_exp(n_valid, m_used, mx, j);
+        if (!spec || pass) break;
         const float m_new = fmaxf(m_used, mx);
         const bool need = (m_new - m_used) * c > 8.f;
-        if (__any_sync(0xffffffffu, need)) {       // rare: this tile raised the max by more than 2^8 -> redo it
-          const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
-          rescale_o(f);
-          l_run *= f;
-          if (need) m_used = m_new;
-          l_tile = tile_exp(n_valid, m_used, mx, j);
-        }
+        if (!__any_sync(0xffffffffu, need)) break;
+        // rare: this tile raised the max by more than 2^8 -> rescale and redo it
+        const float f = need ? ex2f((m_used - m_new) * c) : 1.f;
+        rescale_o(f);
+        l_run *= f;
+        if (need) m_used = m_new;
       }
       l_run += l_tile;
       if (tr) p.trace[j * 16 + 4 * x + 2] = clock64();
+      if (TRACE && lane == 0 && (warp == 1 || warp == 3) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32)
+        p.trace[j * 16 + (warp == 1 ? 3 : 15)] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(x));
@@ -1216,71 +1265,94 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 13) {
     // ===================== MMA issuer =====================
+    // Low-latency form (see attn_fwd3_kernel): this single thread's dependent instruction stream was the period of the
+    // kernel (trace r02: ~3,300 clk per query tile against ~2,500 clk of tensor work; ~250 clk per wait on a barrier that
+    // had completed long before, ~80-100 clk per MMA).  Suspend hint in a register, descriptors = base + immediate,
+    // loops unrolled, stage indices and phases carried incrementally (no division).
     if (role_leader()) {
+      uint32_t hint;
+      asm volatile("mov.u32 %0, %1;" : "=r"(hint) : "r"(p.wait_hint));
+      auto wait = [&](uint32_t bar, uint32_t parity) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok) mbar_wait_h(hint, bar, parity);
+      };
       const int dsteps = p.dpad >> 4;
       const uint32_t idesc_s = make_idesc(128, 0, 0);
       const uint32_t idesc_kv = make_idesc(p.dpad, 0, 1);
       const uint32_t idesc_dq = make_idesc(p.dpad, 1, 1);
-      auto issue_s = [&](int i) {          // S^T_i = K Q_i^T
-        const uint32_t qb = q_smem + (i % AB2_QST) * AT_CHUNK;
-        for (int s = 0; s < dsteps; ++s)
-          tc_mma_bf16(st_tmem, make_desc(k_smem + s * 32, 1024, 0), make_desc(qb + s * 32, 1024, 0), idesc_s, s > 0);
+      constexpr uint64_t MN = (uint64_t)(AT_CHUNK >> 4) << 16;        // leading-dimension byte offset field: MN-major operand
+      constexpr uint64_t STG = AT_CHUNK >> 4;                         // one 16 KB stage in descriptor address units
+      const uint64_t kd = make_desc(k_smem, 1024, 0), vd = make_desc(v_smem, 1024, 0);
+      const uint64_t qd0 = make_desc(q_smem, 1024, 0), dod0 = make_desc(do_smem, 1024, 0), dsd0 = make_desc(ds_smem, 1024, 0);
+      const uint32_t dq0 = dq_tmem(0), dq1 = dq_tmem(1);
+      auto issue_s = [&](uint64_t qd) {    // S^T_i = K Q_i^T
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < dsteps) tc_mma_bf16(st_tmem, kd + 2 * s, qd + 2 * s, idesc_s, s > 0);
         tc_commit(s_full);
       };
-      auto issue_dp = [&](int i) {         // dP^T_i = V dO_i^T
-        const uint32_t dob = do_smem + (i & 1) * AT_CHUNK;
-        for (int s = 0; s < dsteps; ++s)
-          tc_mma_bf16(dp_tmem, make_desc(v_smem + s * 32, 1024, 0), make_desc(dob + s * 32, 1024, 0), idesc_s, s > 0);
+      auto issue_dp = [&](uint64_t dod) {  // dP^T_i = V dO_i^T
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < dsteps) tc_mma_bf16(dp_tmem, vd + 2 * s, dod + 2 * s, idesc_s, s > 0);
         tc_commit(dp_full);
       };
-      mbar_wait_h(p.wait_hint, kv_full, 0);
-      mbar_wait_h(p.wait_hint, q_full(0), 0);
+      wait(kv_full, 0);
+      wait(q_full(0), 0);
       tc_fence_after();
-      issue_s(0);
-      mbar_wait_h(p.wait_hint, do_full(0), 0);
+      issue_s(qd0);
+      wait(do_full(0), 0);
       tc_fence_after();
-      issue_dp(0);
+      issue_dp(dod0);
+      int qs = 0, qph = 0;                 // Q ring stage of tile i and its phase
+#pragma unroll 1
       for (int i = 0; i < TQ; ++i) {
-        const int st = i & 1, qs = i % AB2_QST;
-        const uint32_t qb = q_smem + qs * AT_CHUNK, dob = do_smem + st * AT_CHUNK, dsb = ds_smem + st * 2 * AT_CHUNK;
+        const int st = i & 1;
+        const int qs1 = qs + 1 == AB2_QST ? 0 : qs + 1, qph1 = qs + 1 == AB2_QST ? qph ^ 1 : qph;
+        const uint64_t qd = qd0 + (uint64_t)qs * STG, qd1 = qd0 + (uint64_t)qs1 * STG;
+        const uint64_t dod = dod0 + (uint64_t)st * STG, dod1 = dod0 + (uint64_t)(st ^ 1) * STG;
+        const uint64_t dsd = dsd0 + (uint64_t)st * (2 * STG);
+        const uint32_t acc0 = i > 0 ? 1u : 0u, par = i & 1;
+        const bool more = i + 1 < TQ;
         const bool tr = TRACE && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && i < 32;
         if (tr) p.trace[i * 16 + 8] = clock64();
-        mbar_wait_h(p.wait_hint, p_full, i & 1);
+        wait(p_full, par);
         if (tr) p.trace[i * 16 + 9] = clock64();
         tc_fence_after();
+#pragma unroll
         for (int s = 0; s < 8; ++s)        // dV += P^T_i dO_i: A = P^T from TMEM (queries 0-63 at columns 0.., 64-127 at 64..)
-          tc_mma_bf16_ta(dv_tmem, st_tmem + (s >> 2) * 64 + (s & 3) * 8, make_desc(dob + s * 2048, 1024, AT_CHUNK),
-                         idesc_kv, (i > 0 || s > 0) ? 1u : 0u);
+          tc_mma_bf16_ta(dv_tmem, st_tmem + (s >> 2) * 64 + (s & 3) * 8, (dod | MN) + 128 * s, idesc_kv, s > 0 ? 1u : acc0);
         tc_commit(do_empty(st));           // dO_i has been read for the last time once dV_i retires
-        if (i + 1 < TQ) {                  // the next tile's scores overwrite P^T_i right behind the product that read it
-          mbar_wait_h(p.wait_hint, q_full((i + 1) % AB2_QST), ((i + 1) / AB2_QST) & 1);
+        if (more) {                        // the next tile's scores overwrite P^T_i right behind the product that read it
+          wait(q_full(qs1), qph1);
           tc_fence_after();
-          issue_s(i + 1);
+          issue_s(qd1);
         }
         if (tr) p.trace[i * 16 + 10] = clock64();
-        mbar_wait_h(p.wait_hint, ds_full, i & 1);
+        wait(ds_full, par);
         if (tr) p.trace[i * 16 + 11] = clock64();
         tc_fence_after();
-        for (int s = 0; s < 8; ++s) {      // dK += dS^T_i Q_i
-          const uint32_t aoff = (s >> 2) * AT_CHUNK + (s & 3) * 32;
-          tc_mma_bf16(dk_tmem, make_desc(dsb + aoff, 1024, 0), make_desc(qb + s * 2048, 1024, AT_CHUNK), idesc_kv,
-                      (i > 0 || s > 0) ? 1u : 0u);
-        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)        // dK += dS^T_i Q_i
+          tc_mma_bf16(dk_tmem, dsd + (s >> 2) * STG + (s & 3) * 2, (qd | MN) + 128 * s, idesc_kv, s > 0 ? 1u : acc0);
         if (tr) p.trace[i * 16 + 12] = clock64();
-        mbar_wait_h(p.wait_hint, dq_empty(st), ((i >> 1) & 1) ^ 1);   // the drain warps have read dQ_{i-2}
+        wait(dq_empty(st), ((i >> 1) & 1) ^ 1);   // the drain warps have read dQ_{i-2}
         if (tr) p.trace[i * 16 + 13] = clock64();
         tc_fence_after();
+#pragma unroll
         for (int s = 0; s < 8; ++s)        // dQ_i = dS_i K (reduction over the 128 kv rows)
-          tc_mma_bf16(dq_tmem(st), make_desc(dsb + s * 2048, 1024, AT_CHUNK), make_desc(k_smem + s * 2048, 1024, AT_CHUNK),
-                      idesc_dq, s > 0);
+          tc_mma_bf16(st ? dq1 : dq0, (dsd | MN) + 128 * s, (kd | MN) + 128 * s, idesc_dq, s > 0);
         tc_commit(q_empty(qs));
         tc_commit(dq_full(st));
-        if (i + 1 < TQ) {
-          mbar_wait_h(p.wait_hint, do_full((i + 1) & 1), ((i + 1) >> 1) & 1);
+        if (more) {
+          wait(do_full(st ^ 1), ((i + 1) >> 1) & 1);
           tc_fence_after();
-          issue_dp(i + 1);
+          issue_dp(dod1);
         }
         if (tr) p.trace[i * 16 + 14] = clock64();
+        qs = qs1; qph = qph1;
       }
       tc_commit(done_bar);
     }

@@ -242,35 +242,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One thread's dependent instruction stream: descriptors are base + running offset (no per-MMA field assembly), the
+    // first poll of every wait is inline (phase traces of the attention kernels, r02: ~250 clk per wait and ~55 clk per MMA
+    // of uniform-datapath latency otherwise - more than a 128-wide MMA takes to execute).
     if (role_leader()) {
+      auto wait = [&](uint32_t bar, uint32_t parity) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok) mbar_wait(bar, parity);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase[2] = {0, 0};
+      const uint64_t ad_base = a_mn ? make_desc(smem_base, 1024, 8192) : make_desc(smem_base, 1024, 0);
+      const uint64_t bd_base = b_mn ? make_desc(smem_base + a_bytes, 1024, 8192) : make_desc(smem_base + a_bytes, 1024, 0);
+      const uint64_t a_step = a_mn ? 128 : 2, b_step = b_mn ? 128 : 2;      // one K = 16 step, in 16-byte descriptor units
+      const uint64_t a2_base = make_desc(smem_base + TC_A_BYTES, 1024, 0);  // bm2: second A tile (K-major only)
+      uint64_t stage_off = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
         const int n_mma = b_mn ? ((t.n_valid + 63) & ~63) : ((t.n_valid + 15) & ~15);
         const uint32_t idesc = make_idesc(n_mma, a_mn, b_mn);
-        mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+        wait(tempty_bar(acc), acc_phase[acc] ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0;
+#pragma unroll 1
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          const uint64_t ad = ad_base + stage_off, bd = bd_base + stage_off, a2 = a2_base + stage_off;
+          const uint32_t eb = empty_bar(stage);
+          wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * STB;
-          const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ad = a_mn ? make_desc(sa + k * 2048, 1024, 8192) : make_desc(sa + k * 32, 1024, 0);
-            const uint64_t bd = b_mn ? make_desc(sb + k * 2048, 1024, 8192) : make_desc(sb + k * 32, 1024, 0);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+            tc_mma_bf16(d_tmem, ad + k * a_step, bd + k * b_step, idesc, accumulate);
             // bm2: rows 128..255 of the tile (second A tile, K-major only) against the SAME B tile -> columns 256.. of TMEM
-            if (BM2) tc_mma_bf16(d_tmem + 256, make_desc(sa + TC_A_BYTES + k * 32, 1024, 0), bd, idesc, accumulate);
+            if (BM2) tc_mma_bf16(d_tmem + 256, a2 + 2 * k, bd + k * b_step, idesc, accumulate);
             accumulate = 1;
           }
-          tc_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-          if (++stage == NST) { stage = 0; phase ^= 1; }
+          tc_commit(eb);                 // frees the smem slot when these MMAs retire
+          stage_off += STB >> 4;
+          if (++stage == NST) { stage = 0; phase ^= 1; stage_off = 0; }
         }
         tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         acc_phase[acc] ^= 1;
