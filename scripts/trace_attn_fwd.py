@@ -27,11 +27,10 @@ print("period (A:s_full):", [int(t[j + 1, 1]) - int(t[j, 1]) for j in range(2, 1
 print("A: wait S / exps :", [(int(t[j, 1]) - int(t[j, 0]), int(t[j, 2]) - int(t[j, 1])) for j in range(2, 10)])
 print("B: wait S / exps :", [(int(t[j, 5]) - int(t[j, 4]), int(t[j, 6]) - int(t[j, 5])) for j in range(2, 10)])
 
-dn = ["top", "v_full", "k_full", "pA", "fence", "QKA1", "QKAn", "cmtS", "PVA1", "PVAn", "cmtO", "pB", "QKB", "PVB+c", "end"]
 if int(td.abs().sum()) == 0:
     sys.exit(0)
-print("MMA warp, deltas between consecutive points (clk):")
-print("tile " + " ".join("%6s" % n for n in dn[1:]) + "   total")
+print("per softmax warp (A: 0-3, B: 4-7): scores seen / exponentials done, relative to warp 0's scores-seen of the tile")
 for j in range(3, 12):
-    v = [int(td[j, i]) for i in range(15)]
-    print("%4d " % j + " ".join("%6d" % (v[i] - v[i - 1]) for i in range(1, 15)) + "  %6d" % (int(td[j + 1, 0]) - v[0]))
+    b0 = int(td[j, 8])
+    print("%4d  seen " % j + " ".join("%6d" % (int(td[j, 8 + w]) - b0) for w in range(8)) +
+          "   done " + " ".join("%6d" % (int(td[j, w]) - b0) for w in range(8)))

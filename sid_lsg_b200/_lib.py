@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "sidlsg.h")
-LIB_PATH = os.path.join(_HERE, "_C", "libsidlsg.so")
+LIB_PATH = os.environ.get("SIDLSG_LIB") or os.path.join(_HERE, "_C", "libsidlsg.so")   # SIDLSG_LIB: A/B builds side by side
 
 F32, BF16 = 0, 1
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
