@@ -81,7 +81,7 @@ if which in ("all", "conv"):
         timeit(lambda: y2.backward(dy, retain_graph=True), fl, name="  wgrad")
 
 if which in ("all", "gn"):
-    for (B, HW, C) in ((32, 4096, 320), (32, 1024, 640), (32, 4096, 960)):
+    for (B, HW, C) in ((64, 4096, 320), (64, 1024, 640), (64, 256, 1280), (64, 4096, 960), (32, 4096, 320)):
         x = torch.randn(B, HW, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
         g = torch.nn.Parameter(torch.ones(C, device=dev)); bt = torch.nn.Parameter(torch.zeros(C, device=dev))
         n = B * HW * C * 2.0
