@@ -89,3 +89,21 @@ if which in ("all", "gn"):
         y = ops.group_norm(x, g, bt, 32, 1e-5, True)
         dy = torch.randn_like(y)
         timeit(lambda: torch.autograd.grad(y, (x,), dy, retain_graph=True), nbytes=5 * n, name="  gn bwd")
+
+if which in ("all", "ln"):
+    for (M, C) in ((262144, 320), (65536, 640), (16384, 1280)):
+        x = torch.randn(M, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        g = torch.nn.Parameter(torch.ones(C, device=dev)); bt = torch.nn.Parameter(torch.zeros(C, device=dev))
+        g.grad = torch.zeros_like(g); bt.grad = torch.zeros_like(bt)
+        n = M * C * 2.0
+        timeit(lambda: ops.layer_norm(x.detach(), g, bt, 1e-5), nbytes=2 * n, name="ln fwd M%d C%d" % (M, C))
+        y = ops.layer_norm(x, g, bt, 1e-5)
+        dy = torch.randn_like(y)
+        timeit(lambda: torch.autograd.grad(y, (x,), dy, retain_graph=True), nbytes=3 * n, name="  ln bwd")
+    for (M, F) in ((262144, 1280), (65536, 2560), (16384, 5120)):
+        x = torch.randn(M, 2 * F, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        n = M * F * 2.0
+        timeit(lambda: ops.GegluFn.apply(x.detach()), nbytes=3 * n, name="geglu fwd M%d F%d" % (M, F))
+        y = ops.GegluFn.apply(x)
+        dy = torch.randn_like(y)
+        timeit(lambda: torch.autograd.grad(y, (x,), dy, retain_graph=True), nbytes=5 * n, name="  geglu bwd")
