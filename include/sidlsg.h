@@ -197,6 +197,9 @@ int sidlsg_narrow_col2im(const void* col, int ld, void* y, const float* bias, in
 int sidlsg_pad2d(const void* src, long lds, void* dst, int R, int K, int Rp, int Kp, void* stream);
 int sidlsg_add_transposed(const float* src, int lds, float* dst, int R, int K, void* stream);
 
+/* Debug: tensor-core GEMM / conv launches after this call stamp clock64 at the phase boundaries of CTA 1's first 32
+ * tiles into trace (device, 32 x 16 int64; scripts/trace_gemm.py); null switches the stamps off. */
+int sidlsg_debug_gemm_trace(void* trace);
 /* development aid: attention forward (d <= 64) with in-kernel clock64 stamps (32 x 16 long long, device memory) */
 int sidlsg_debug_attention_fwd_trace(const void* q, const void* k, const void* v, void* o, float* lse, int B,
                                      int N, int M, int H, int d, long ldq, long ldk, long ldv, void* trace,

@@ -16,6 +16,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", CSRC, "-I", INCLUDE]
+# extra compile flags for instrumented builds, e.g. SIDLSG_NVCC_EXTRA=-DSIDLSG_GEMM_TRACE (scripts/trace_gemm.py); use --force
+NVCC_FLAGS += os.environ.get("SIDLSG_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -70,6 +70,7 @@ struct TcParams {
   int stages;               // smem ring depth: floor(192 KB / (16 KB + B tile bytes)), 4..8
   int stage_bytes;          // 16 KB A tile + B tile (block_n rows x 128 B, or 64-column boxes x 8 KB for MN-major B)
   int tma_store;            // bf16 output leaves through smem staging + TMA bulk stores (tmC) instead of per-row stores
+  long long* trace;         // phase trace of CTA 1 (sidlsg_debug_gemm_trace; null in production)
   // batched dense GEMMs (attention score / value contractions per (batch, head)): 4-D operand maps
   // (inner, outer, nb2, nb1); tile index = ((batch * m_tiles) + m) * n_tiles + n
   int batched, nb2;
@@ -89,19 +90,8 @@ struct TileInfo {
   int m0, n_in, col0, n_valid, tap, kb0, kb1, b1, b2;
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
+__device__ __forceinline__ TileInfo tile_from_blocks(const TcParams& p, int m_blk, int n_blk, int split, int per) {
   TileInfo t;
-  // split-K tiles are ordered split-major: the CTAs running at the same time work on the SAME K slab for different
-  // (m, n) output tiles, so the operand slabs are fetched from HBM once and shared through L2 (with the split index
-  // innermost every concurrent CTA streamed its own slab: 300 MB of DRAM reads for 168 MB of operands)
-  int split = 0, r = tile;
-  if (p.splits > 1) {
-    const int base = p.m_tiles * p.n_tiles;
-    split = tile / base;
-    r = tile - split * base;
-  }
-  int n_blk = r % p.n_tiles;
-  int m_blk = r / p.n_tiles;
   t.b1 = t.b2 = 0;
   if (p.batched) {
     const int bidx = m_blk / p.m_tiles;
@@ -121,11 +111,48 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
     t.col0 = t.n_in;
     t.n_valid = min(p.block_n, p.N - t.n_in);
   }
-  int per = (p.kb_total + p.splits - 1) / p.splits;
   t.kb0 = split * per;
   t.kb1 = min(p.kb_total, t.kb0 + per);
   return t;
 }
+
+// Walks the tiles blockIdx.x, + gridDim.x, ... of the persistent grid.  Tile index -> (split, m block, n block) costs
+// three integer divisions (~100 clk of dependent SASS each); the phase trace of the K = 320 GEMMs showed ~1,500 clk
+// between the last chunk of one tile and the first of the next in the EPILOGUE warps, which bound those tiles.  The
+// cursor divides once and then steps (m, n) by (stride / n_tiles, stride % n_tiles) with a carry.
+// Phase-trace stamps (scripts/trace_gemm.py) are compiled in only with -DSIDLSG_GEMM_TRACE (SIDLSG_NVCC_EXTRA of build.py):
+// even switched off at run time they cost the conv tiles ~1 % (same-box A/B).
+#ifdef SIDLSG_GEMM_TRACE
+#define SIDLSG_TRACE_ON 1
+#else
+#define SIDLSG_TRACE_ON 0
+#endif
+struct TileCursor {
+  int tile, m_blk, n_blk, split, dq, dr, per, stride, rows;
+  __device__ __forceinline__ TileCursor(const TcParams& p, int tile0, int stride_) {
+    tile = tile0; stride = stride_;
+    rows = p.m_tiles * (p.batched ? p.batched : 1);               // m blocks per split (batches folded into m)
+    const int base = rows * p.n_tiles;                            // (m, n) tiles per split
+    per = (p.kb_total + p.splits - 1) / p.splits;
+    // split-K tiles are ordered split-major: the CTAs running at the same time work on the SAME K slab for different
+    // (m, n) output tiles, so the operand slabs are fetched from HBM once and shared through L2 (with the split index
+    // innermost every concurrent CTA streamed its own slab: 300 MB of DRAM reads for 168 MB of operands)
+    split = tile0 / base;
+    const int r = tile0 - split * base;
+    m_blk = r / p.n_tiles;
+    n_blk = r - m_blk * p.n_tiles;
+    dq = stride / p.n_tiles;
+    dr = stride - dq * p.n_tiles;
+  }
+  __device__ __forceinline__ TileInfo info(const TcParams& p) const { return tile_from_blocks(p, m_blk, n_blk, split, per); }
+  __device__ __forceinline__ void advance(const TcParams& p) {
+    tile += stride;
+    n_blk += dr;
+    m_blk += dq;
+    if (n_blk >= p.n_tiles) { n_blk -= p.n_tiles; ++m_blk; }
+    while (m_blk >= rows) { m_blk -= rows; ++split; }
+  }
+};
 
 template <bool BM2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -180,8 +207,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(p, tile);
+      int tix = 0;
+      for (TileCursor cur(p, blockIdx.x, gridDim.x); cur.tile < total_tiles; cur.advance(p), ++tix) {
+        const TileInfo t = cur.info(p);
+        if (SIDLSG_TRACE_ON && p.trace && blockIdx.x == 1 && tix < 32) p.trace[tix * 16 + 15] = clock64();
         int ab0 = 0, ah0 = 0, ab1 = 0, ah1 = 0;
         if (p.a_mode == A_CONV) {
           ab0 = t.m0 / hw; ah0 = (t.m0 - ab0 * hw) / p.W;
@@ -261,12 +290,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint64_t a_step = a_mn ? 128 : 2, b_step = b_mn ? 128 : 2;      // one K = 16 step, in 16-byte descriptor units
       const uint64_t a2_base = make_desc(smem_base + TC_A_BYTES, 1024, 0);  // bm2: second A tile (K-major only)
       uint64_t stage_off = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(p, tile);
+      int tix = 0;
+      for (TileCursor cur(p, blockIdx.x, gridDim.x); cur.tile < total_tiles; cur.advance(p), ++tix) {
+        const TileInfo t = cur.info(p);
         const int n_mma = b_mn ? ((t.n_valid + 63) & ~63) : ((t.n_valid + 15) & ~15);
         const uint32_t idesc = make_idesc(n_mma, a_mn, b_mn);
+        long long* tr = (SIDLSG_TRACE_ON && p.trace && blockIdx.x == 1 && tix < 32) ? p.trace + tix * 16 : nullptr;
         wait(tempty_bar(acc), acc_phase[acc] ^ 1);
         tc_fence_after();
+        if (tr) tr[12] = clock64();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0;
 #pragma unroll 1
@@ -275,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t eb = empty_bar(stage);
           wait(full_bar(stage), phase);
           tc_fence_after();
+          if (tr && kb == t.kb0) tr[13] = clock64();
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             tc_mma_bf16(d_tmem, ad + k * a_step, bd + k * b_step, idesc, accumulate);
@@ -287,6 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == NST) { stage = 0; phase ^= 1; stage_off = 0; }
         }
         tc_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        if (tr) tr[14] = clock64();
         acc_phase[acc] ^= 1;
         if (!BM2) acc ^= 1;            // bm2: both TMEM halves belong to one tile (single-buffered)
       }
@@ -299,9 +333,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase[2] = {0, 0};
     uint32_t ochunk = 0;                 // output chunks staged so far (staging buffer = parity)
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileInfo t = decode_tile(p, tile);
+    // tile-invariant half of the fast-path test (the phase trace showed ~850 clk of scalar code per tile between the
+    // top of the epilogue loop and the accumulator wait: this predicate, re-evaluated from the constant bank every tile)
+    const bool fast_inv = (p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0)) &&
+                          ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
+                          (((p.c_sb1 | p.c_sb2) & (p.out_f32 ? 3 : 7)) == 0) &&
+                          (!p.res || (((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
+                          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                          (!p.rowvec || (((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0)));
+    // Staging-buffer hand-over.  Short reductions (<= 8 k-blocks per tile: the K = 320 / 512 GEMMs, whose tiles are bound by
+    // THIS loop) use ONE named barrier per 64-column chunk: before it the leader waits until every bulk store issued so far
+    // has read its buffer, so after it the next chunk may overwrite the older buffer at once.  Deep reductions (conv3x3,
+    // K >= 640) keep two barriers per chunk with the relaxed wait (all but the latest store): their stores queue behind the
+    // main loop's TMA loads and the strict wait stalled all eight warps (conv 0.194 -> 0.202 ms, same-box A/B).
+    const bool one_bar = ((p.kb_total + p.splits - 1) / p.splits) <= 8;
+    int tix = 0;
+    for (TileCursor cur(p, blockIdx.x, gridDim.x); cur.tile < total_tiles; cur.advance(p), ++tix) {
+      const TileInfo t = cur.info(p);
       const int nhalf = BM2 ? 2 : 1;
+      long long* tr = (SIDLSG_TRACE_ON && p.trace && blockIdx.x == 1 && threadIdx.x == 128 && tix < 32) ? p.trace + tix * 16 : nullptr;
+      if (tr) tr[0] = clock64();
       for (int half = 0; half < nhalf; ++half) {     // bm2: rows 0-127 (TMEM columns 0..) then rows 128-255 (columns 256..)
       const int m = t.m0 + half * TC_BM + q * 32 + lane;
       const bool row_ok = m < p.M;
@@ -310,13 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long crow = (long)m * p.ldc + t.col0 + t.b1 * p.c_sb1 + t.b2 * p.c_sb2;
       const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long)(m / p.rows_per_vec) * p.N + t.col0 : nullptr;
       // fast path: whole 16-column groups, 16-byte aligned rows (every shape of the UNet)
-      const bool fast = ((t.n_valid & 15) == 0) && ((t.col0 & 15) == 0) &&
-                        (p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0)) &&
-                        ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
-                        (((p.c_sb1 | p.c_sb2) & (p.out_f32 ? 3 : 7)) == 0) &&
-                        (!p.res || (((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
-                        (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-                        (!p.rowvec || (((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0)));
+      const bool fast = fast_inv && ((t.n_valid & 15) == 0) && ((t.col0 & 15) == 0);
       // bf16 residual of this thread's columns, fetched BEFORE the accumulator is complete: the DRAM latency of the
       // residual tile hides behind the main loop instead of serialising the epilogue (K = 320 GEMMs are output-bound)
       uint4 rpre[16];
@@ -340,13 +385,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ts && p.bias && half == 0) {
         // bias of this tile's columns -> smem while the main loop is still running (the per-chunk __ldg's were the
         // epilogue's largest stall).  Single buffer: every read of the previous tile's bias precedes that tile's last
-        // named barrier, every read of this one follows the first barrier below.
+        // named barrier, every read of this one follows the barrier here.
         const int j = threadIdx.x - 128;
         if (j < t.n_valid) bias_s[j] = __ldg(p.bias + t.col0 + j);
+        if (one_bar) named_bar_sync(1, 256);       // (two-barrier mode: the first chunk's buffer barrier separates them)
       }
       if (half == 0) {
-        mbar_wait(tfull_bar(acc), acc_phase[acc]);
+        mbar_wait(tfull_bar(acc), acc_phase[acc]);   // (all lanes poll: lane-0 polling + __syncwarp measured 20 % SLOWER on K = 320 N = 2560)
         tc_fence_after();
+        if (tr) tr[1] = clock64();
       }
       if (ts) {
         // ---- staged epilogue: 64-column chunks -> bf16 SWIZZLE_128B smem tile -> ONE TMA bulk store per chunk (128-byte
@@ -366,9 +413,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t obuf = out_base + (uint32_t)(ochunk & 1) * TC_OUT_BYTES;
           if (!direct) {
             ++ochunk;
-            if (leader) tma_wait_group_read1();     // the store that used this buffer two chunks ago has read it
-            named_bar_sync(1, 256);
+            if (!one_bar) {
+              if (leader) tma_wait_group_read1();   // the store that used this buffer two chunks ago has read it
+              named_bar_sync(1, 256);
+            }
           }
+          if (tr && half == 0 && ci < 3) tr[2 + 3 * ci] = clock64();
           const int c = c64 + grp * 32;
           if (c < t.n_valid) {
             const bool two = c + 32 <= t.n_valid;   // 32 columns, or a 16-column tail
@@ -428,14 +478,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (tr && half == 0 && ci < 3) tr[3 + 3 * ci] = clock64();
           if (!direct) {
             fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
-            named_bar_sync(2, 256);
+            if (one_bar && leader) tma_wait_group_read0();   // the previous chunk's store (issued a whole chunk ago) has read its
+            named_bar_sync(2, 256);                          // buffer: after this barrier the NEXT chunk may overwrite it
             if (leader) {
               tma_store_2d(&tmC, obuf, t.col0 + c64, t.m0 + half * TC_BM);
               tma_commit_group();
             }
           }
+          if (tr && half == 0 && ci < 3) tr[4 + 3 * ci] = clock64();
         }
         // a direct tail chunk has no barrier behind it: without this one a fast warp could stage the NEXT tile's bias
         // while a slow warp still reads this tile's
@@ -548,6 +601,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       }   // half
+      if (tr) tr[11] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -810,9 +864,12 @@ static void plan_stages(TcParams& p) {
   p.stages = ns > TC_MAX_STAGES ? TC_MAX_STAGES : (ns < 2 ? 2 : ns);
 }
 
+static long long* g_gemm_trace = nullptr;   // sidlsg_debug_gemm_trace: device buffer [32 tiles][16 slots] stamped by CTA 1
+
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, TcParams& p, cudaStream_t st) {
   long tiles = (long)p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
   if (tiles <= 0) return SIDLSG_OK;
+  p.trace = g_gemm_trace;
   __atomic_add_fetch(&g_tc_launches, 1, __ATOMIC_RELAXED);
   g_last_path = 1;
   int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
@@ -1094,5 +1151,12 @@ extern "C" int sidlsg_last_path() { return sidlsg::g_last_path; }
 extern "C" int sidlsg_counters(long* out) {
   out[0] = sidlsg::g_tc_launches;
   out[1] = sidlsg::g_simt_launches;
+  return SIDLSG_OK;
+}
+
+// Debug: GEMM / conv launches after this call stamp clock64 at the phase boundaries of CTA 1's first 32 tiles into
+// `trace` (device, 32 x 16 int64; scripts/trace_gemm.py); null switches the stamps off again.
+extern "C" int sidlsg_debug_gemm_trace(void* trace) {
+  sidlsg::g_gemm_trace = (long long*)trace;
   return SIDLSG_OK;
 }
