@@ -197,6 +197,10 @@ int sidlsg_narrow_col2im(const void* col, int ld, void* y, const float* bias, in
 int sidlsg_pad2d(const void* src, long lds, void* dst, int R, int K, int Rp, int Kp, void* stream);
 int sidlsg_add_transposed(const float* src, int lds, float* dst, int R, int K, void* stream);
 
+/* Debug / test (host only, no GPU): the tiles CTA `cta` of a `grid`-CTA persistent GEMM launch visits, walked with the
+ * kernel's own tile cursor.  geom[9] = {m_tiles, n_tiles, splits, batched, nb2, kb_total, block_n, N, bm2}; out: up to
+ * max_tiles records of 8 ints {tile, m0, col0, n_valid, kb0, kb1, b1, b2}.  Returns the number of tiles (< 0: error). */
+int sidlsg_debug_tile_walk(const int* geom, int cta, int grid, int max_tiles, int* out);
 /* Debug: tensor-core GEMM / conv launches after this call stamp clock64 at the phase boundaries of CTA 1's first 32
  * tiles into trace (device, 32 x 16 int64; scripts/trace_gemm.py); null switches the stamps off. */
 int sidlsg_debug_gemm_trace(void* trace);

@@ -90,7 +90,7 @@ struct TileInfo {
   int m0, n_in, col0, n_valid, tap, kb0, kb1, b1, b2;
 };
 
-__device__ __forceinline__ TileInfo tile_from_blocks(const TcParams& p, int m_blk, int n_blk, int split, int per) {
+__host__ __device__ __forceinline__ TileInfo tile_from_blocks(const TcParams& p, int m_blk, int n_blk, int split, int per) {
   TileInfo t;
   t.b1 = t.b2 = 0;
   if (p.batched) {
@@ -129,7 +129,7 @@ __device__ __forceinline__ TileInfo tile_from_blocks(const TcParams& p, int m_bl
 #endif
 struct TileCursor {
   int tile, m_blk, n_blk, split, dq, dr, per, stride, rows;
-  __device__ __forceinline__ TileCursor(const TcParams& p, int tile0, int stride_) {
+  __host__ __device__ __forceinline__ TileCursor(const TcParams& p, int tile0, int stride_) {
     tile = tile0; stride = stride_;
     rows = p.m_tiles * (p.batched ? p.batched : 1);               // m blocks per split (batches folded into m)
     const int base = rows * p.n_tiles;                            // (m, n) tiles per split
@@ -144,8 +144,8 @@ struct TileCursor {
     dq = stride / p.n_tiles;
     dr = stride - dq * p.n_tiles;
   }
-  __device__ __forceinline__ TileInfo info(const TcParams& p) const { return tile_from_blocks(p, m_blk, n_blk, split, per); }
-  __device__ __forceinline__ void advance(const TcParams& p) {
+  __host__ __device__ __forceinline__ TileInfo info(const TcParams& p) const { return tile_from_blocks(p, m_blk, n_blk, split, per); }
+  __host__ __device__ __forceinline__ void advance(const TcParams& p) {
     tile += stride;
     n_blk += dr;
     m_blk += dq;
@@ -1159,4 +1159,29 @@ extern "C" int sidlsg_counters(long* out) {
 extern "C" int sidlsg_debug_gemm_trace(void* trace) {
   sidlsg::g_gemm_trace = (long long*)trace;
   return SIDLSG_OK;
+}
+
+// Debug / test: the tiles CTA `cta` of a `grid`-CTA persistent launch visits, walked on the HOST with the kernel's own
+// TileCursor.  geom[9] = {m_tiles, n_tiles, splits, batched, nb2, kb_total, block_n, N, bm2}; out receives up to
+// max_tiles records of 8 ints {tile, m0, col0, n_valid, kb0, kb1, b1, b2}; returns the number of tiles (tests compare it
+// with the division-per-tile decode the cursor replaced).
+extern "C" int sidlsg_debug_tile_walk(const int* geom, int cta, int grid, int max_tiles, int* out) {
+  using namespace sidlsg;
+  if (!geom || !out || grid <= 0 || cta < 0 || cta >= grid || geom[0] <= 0 || geom[1] <= 0 || geom[2] <= 0 || geom[6] <= 0) {
+    set_error("sidlsg_debug_tile_walk: bad arguments");
+    return SIDLSG_ERR_ARG;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = geom[0]; p.n_tiles = geom[1]; p.splits = geom[2]; p.batched = geom[3]; p.nb2 = geom[4] > 0 ? geom[4] : 1;
+  p.kb_total = geom[5]; p.block_n = geom[6]; p.N = geom[7]; p.bm2 = geom[8];
+  p.b_mode = B_K2D;
+  const int total = p.m_tiles * p.n_tiles * p.splits * (p.batched ? p.batched : 1);
+  int n = 0;
+  for (TileCursor cur(p, cta, grid); cur.tile < total && n < max_tiles; cur.advance(p), ++n) {
+    const TileInfo t = cur.info(p);
+    int* o = out + 8 * n;
+    o[0] = cur.tile; o[1] = t.m0; o[2] = t.col0; o[3] = t.n_valid; o[4] = t.kb0; o[5] = t.kb1; o[6] = t.b1; o[7] = t.b2;
+  }
+  return n;
 }

@@ -86,3 +86,54 @@ def test_split_k_fills_the_grid_without_a_ragged_last_wave():
         assert tiles >= 100, p
         frac = waves - int(waves)
         assert frac == 0 or frac >= 0.6 or waves < 1, (p, tiles)
+
+
+# ---- tile cursor of the persistent GEMM (sidlsg_debug_tile_walk runs the kernel's own TileCursor on the host) ----------
+def _walk(geom, cta, grid, max_tiles=4096):
+    lib.load()
+    g = (ctypes.c_int * 9)(*geom)
+    out = (ctypes.c_int * (8 * max_tiles))()
+    n = lib._fns["sidlsg_debug_tile_walk"](g, cta, grid, max_tiles, out)
+    assert n >= 0, lib.last_error()
+    return [tuple(out[8 * i: 8 * i + 8]) for i in range(n)]
+
+
+def _decode(geom, tile):
+    """the division-per-tile decode the cursor replaced (sid_lsg_b200/csrc/gemm_tc.cu history)"""
+    m_tiles, n_tiles, splits, batched, nb2, kb_total, block_n, N, bm2 = geom
+    base = m_tiles * n_tiles * (batched if batched else 1)
+    split, r = divmod(tile, base)
+    m_blk, n_blk = divmod(r, n_tiles)
+    b1 = b2 = 0
+    if batched:
+        bidx, m_blk = divmod(m_blk, m_tiles)
+        b1, b2 = divmod(bidx, nb2 if nb2 > 0 else 1)
+    m0 = m_blk * (256 if bm2 else 128)
+    n_in = n_blk * block_n
+    per = (kb_total + splits - 1) // splits
+    kb0 = split * per
+    return (tile, m0, n_in, min(block_n, N - n_in), kb0, min(kb_total, kb0 + per), b1, b2)
+
+
+@pytest.mark.parametrize("geom,grid", [
+    ((2048, 2, 1, 0, 0, 5, 160, 320, 0), 148),      # M262144 N320 K320: two 160-wide tiles per row block
+    ((1024, 3, 1, 0, 0, 10, 256, 640, 0), 148),     # N640 as 256 + 256 + 128
+    ((512, 10, 1, 0, 0, 5, 256, 2560, 1), 148),     # 256-row tiles
+    ((3, 3, 37, 0, 0, 4096, 128, 320, 0), 148),     # split-K weight gradient: split-major order, ragged last split
+    ((5, 7, 4, 0, 0, 1023, 96, 640, 0), 111),       # stride > tiles per split, stride % n_tiles != 0
+    ((2, 1, 1, 512, 8, 3, 80, 77, 0), 148),         # batched (attention scores of the exact path): B x heads problems
+    ((1, 1, 1, 0, 0, 1, 16, 16, 0), 148),           # fewer tiles than CTAs
+    ((7, 5, 3, 6, 2, 11, 64, 300, 0), 13),          # everything at once
+])
+def test_tile_cursor_matches_division_decode(geom, grid):
+    m_tiles, n_tiles, splits, batched = geom[:4]
+    total = m_tiles * n_tiles * splits * (batched if batched else 1)
+    seen = []
+    for cta in sorted({0, 1, grid // 2, grid - 1}):
+        got = _walk(geom, cta, grid)
+        want = [_decode(geom, t) for t in range(cta, total, grid)]
+        assert got == want, (geom, grid, cta, got[:3], want[:3])
+        seen += [g[0] for g in got]
+    if grid <= 16:      # every tile exactly once over the whole grid
+        allt = sorted(t for cta in range(grid) for (t, *_rest) in _walk(geom, cta, grid))
+        assert allt == list(range(total))
