@@ -19,7 +19,7 @@ def _latest(pattern):
 
 
 def test_own_arm_record_has_the_contract_keys():
-    d = _latest("r02_bench_final*_n1.json")
+    d = _latest("r02_bench_final[0-9]*_n1.json")
     for k in BASE + ("roofline", "clocks"):
         assert k in d, k
     assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["n_gpus"] == 1
@@ -43,8 +43,8 @@ def test_own_arm_record_has_the_contract_keys():
 
 
 def test_reference_arm_record():
-    d = _latest("r02_bench_reference_arm_final*.json")
-    own = _latest("r02_bench_final*_n1.json")
+    d = _latest("r02_bench_reference_arm_final[0-9]*.json")
+    own = _latest("r02_bench_final[0-9]*_n1.json")
     for k in BASE + ("impl",):
         assert k in d, k
     assert d["impl"] == "reference"
@@ -57,5 +57,5 @@ def test_reference_arm_record():
 
 def test_metric_is_the_baseline_metric():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    d = _latest("r02_bench_final*_n1.json")
+    d = _latest("r02_bench_final[0-9]*_n1.json")
     assert d["metric"].split(" (")[0] in base["metric"]
